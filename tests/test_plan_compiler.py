@@ -1,0 +1,52 @@
+"""Host-side term compiler (plan.py) against the oracle, on the CPU: the compiled tables, interpreted
+with numpy, must reproduce the oracle's basis matrices for every parity workload."""
+
+import numpy as np
+import pytest
+
+from cases import cases, fresh_kwargs
+from harness import rel_err
+from plan_interp import PlanInterp
+from ttm_oracle import OracleMap
+from ttt_b200.plan import ComponentPlan, resolve_family
+
+CASES = cases()
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_compiled_tables_reproduce_oracle_basis(name):
+    case = CASES[name]
+    kw = fresh_kwargs(case)
+    om = OracleMap(X=case['X'].copy(), **kw)
+    fam, polyfunc, polyder, _ = resolve_family(kw.get('polynomial_type', 'hermite function'))
+    sep = kw['monotonicity'].startswith('sep')
+    Dtot = case['X'].shape[1]
+    for k in range(om.D):
+        c = k + om.skip_dimensions
+        plan = ComponentPlan(k, c, Dtot, fam, polyfunc, polyder, kw['monotone'][k], kw['nonmonotone'][k],
+                             om.special_terms, kw.get('linearization'))
+        it = PlanInterp(plan.iblob, plan.dblob)
+        assert rel_err(it.terms(0, om.X), om.Psi_nonmon[k]) <= 1e-12
+        assert rel_err(it.terms(1, om.X), om.Psi_mon[k]) <= 1e-12
+        assert rel_err(it.nonmon_structured(om.X), om.Psi_nonmon[k]) <= 1e-12
+        assert rel_err(it.mon_structured(om.X), om.Psi_mon[k]) <= 1e-12
+        if sep:
+            assert rel_err(it.terms(2, om.X), om.der_Psi_mon[k]) <= 1e-12
+            assert np.array_equal(plan.lb, om.optimization_constraints_lb[k])
+            assert np.array_equal(plan.ub, om.optimization_constraints_ub[k])
+        assert plan.m_mon == len(om.coeffs_mon[k]) and plan.m_non == len(om.coeffs_nonmon[k])
+        # alignment contract of the vector-loaded records
+        h = plan.iblob
+        from ttt_b200 import plan as PL
+        assert h[PL.H_FAC_I] % 4 == 0 and h[PL.H_ENT_I] % 4 == 0 and h[PL.H_VAR_IDX] % 2 == 0
+        assert h[PL.H_D_FAC] % 4 == 0 and h[PL.H_D_ENT] % 4 == 0
+
+
+def test_bad_options_raise_like_the_reference():
+    with pytest.raises(Exception, match='Polynomial type not understood'):
+        resolve_family('fourier')
+    from ttt_b200.plan import parse_entry
+    with pytest.raises(ValueError, match='not understood'):
+        parse_entry('XBF 0', np.zeros(2, dtype=int), 0, True, None)
+    with pytest.raises(Exception, match="'LIN' modifier"):
+        parse_entry([0, 'LIN'], np.zeros(2, dtype=int), 0, True, None)

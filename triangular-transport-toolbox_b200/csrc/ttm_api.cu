@@ -1,0 +1,426 @@
+// C ABI of libttm (see include/ttm.h).  Thin: argument checks, device selection, workspace
+// ownership, kernel launches.  No torch types, no exceptions across the boundary.
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ttm.h"
+#include "ttm_kernels.h"
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return TTM_ERR_CUDA;
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);          \
+    } while (0)
+
+constexpr int MAX_GRID = 148 * 8;
+}  // namespace
+
+struct ttm_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int Q = 0;
+    double wsum = 0.0;
+    double* d_xis = nullptr;
+    double* d_ws = nullptr;
+    int rect = RECT_EXP;
+    double delta = 1e-8;
+    int* d_flags = nullptr;   // [0] iter_max, [1] not_converged
+};
+
+struct ttm_plan {
+    ttm_ctx* ctx = nullptr;
+    PlanView view{};
+    int32_t* d_ib = nullptr;
+    double* d_db = nullptr;
+    int64_t n_int = 0, n_double = 0;
+    int m = 0;
+    double* d_coeffs = nullptr;    // [m]
+    double* d_out = nullptr;       // [1+m]
+    double* d_partials = nullptr;  // [MAX_GRID][1+m]
+    unsigned int* d_counter = nullptr;
+    double* h_pin = nullptr;       // pinned staging [2*(1+m)]
+};
+
+extern "C" {
+
+const char* ttm_last_error(void) { return g_err.c_str(); }
+int ttm_version(void) { return 100; }
+
+int ttm_device_sm_count(int device, int* host_sm_count) {
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    *host_sm_count = p.multiProcessorCount;
+    return TTM_OK;
+}
+
+int ttm_ctx_create(int device, ttm_ctx** host_out) {
+    if (!host_out) return fail(TTM_ERR_ARG, "ttm_ctx_create: null output");
+    CK(cudaSetDevice(device));
+    auto* c = new ttm_ctx();
+    c->device = device;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    c->sm_count = p.multiProcessorCount;
+    CK(cudaMalloc(&c->d_flags, 2 * sizeof(int)));
+    CK(cudaMemset(c->d_flags, 0, 2 * sizeof(int)));
+    *host_out = c;
+    return TTM_OK;
+}
+
+int ttm_ctx_destroy(ttm_ctx* c) {
+    if (!c) return TTM_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_xis);
+    cudaFree(c->d_ws);
+    cudaFree(c->d_flags);
+    delete c;
+    return TTM_OK;
+}
+
+int ttm_ctx_set_quadrature(ttm_ctx* c, const double* host_xis, const double* host_ws, int Q) {
+    if (!c || !host_xis || !host_ws || Q <= 0) return fail(TTM_ERR_ARG, "ttm_ctx_set_quadrature: bad arguments");
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->d_xis);
+    cudaFree(c->d_ws);
+    CK(cudaMalloc(&c->d_xis, Q * sizeof(double)));
+    CK(cudaMalloc(&c->d_ws, Q * sizeof(double)));
+    CK(cudaMemcpy(c->d_xis, host_xis, Q * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_ws, host_ws, Q * sizeof(double), cudaMemcpyHostToDevice));
+    c->Q = Q;
+    double s = 0.0;
+    for (int q = 0; q < Q; ++q) s += host_ws[q];
+    c->wsum = s;
+    return TTM_OK;
+}
+
+int ttm_ctx_set_rectifier(ttm_ctx* c, int rect, double delta) {
+    if (!c || rect < 0 || rect > RECT_ELU) return fail(TTM_ERR_ARG, "ttm_ctx_set_rectifier: bad arguments");
+    c->rect = rect;
+    c->delta = delta;
+    return TTM_OK;
+}
+
+static int parse_view(ttm_plan* p, const int32_t* h) {
+    if (p->n_int < H_SIZE || h[H_MAGIC] != TTM_PLAN_MAGIC) return fail(TTM_ERR_ARG, "ttm_plan_create: bad plan blob");
+    PlanView& v = p->view;
+    v.ib = p->d_ib;
+    v.db = p->d_db;
+    v.dtot = h[H_DTOT]; v.c = h[H_C]; v.family = h[H_FAMILY]; v.nfac = h[H_NFAC];
+    v.m_non = h[H_M_NON]; v.m_mon = h[H_M_MON]; v.m_dmon = h[H_M_DMON];
+    v.nconst = h[H_NCONST]; v.nvars = h[H_NVARS]; v.nmulti = h[H_NMULTI];
+    v.maxord = h[H_MAXORD]; v.has_plain = h[H_HAS_PLAIN]; v.has_hf = h[H_HAS_HF]; v.nst = h[H_NST];
+    v.nslot = h[H_NSLOT];
+    v.o_fac_i = h[H_FAC_I];
+    v.o_non_ptr = h[H_NON_PTR]; v.o_non_fac = h[H_NON_FAC];
+    v.o_mon_ptr = h[H_MON_PTR]; v.o_mon_fac = h[H_MON_FAC];
+    v.o_dmon_ptr = h[H_DMON_PTR]; v.o_dmon_fac = h[H_DMON_FAC];
+    v.o_const_idx = h[H_CONST_IDX]; v.o_var_idx = h[H_VAR_IDX]; v.o_var_ptr = h[H_VAR_PTR];
+    v.o_ent_i = h[H_ENT_I]; v.o_multi_idx = h[H_MULTI_IDX];
+    v.o_slot_ptr = h[H_SLOT_PTR]; v.o_slot_term = h[H_SLOT_TERM];
+    v.o_out_ptr = h[H_OUT_PTR]; v.o_out_fac = h[H_OUT_FAC]; v.o_st_fac = h[H_ST_FAC];
+    v.o_d_fac = h[H_D_FAC]; v.o_d_ent = h[H_D_ENT]; v.o_d_slot_scale = h[H_D_SLOT_SCALE]; v.o_d_rec = h[H_D_REC];
+    // alignment of the vector-loaded records
+    if ((v.o_fac_i & 3) || (v.o_ent_i & 3) || (v.o_var_idx & 1) || (v.o_d_fac & 3) || (v.o_d_ent & 3))
+        return fail(TTM_ERR_ARG, "ttm_plan_create: misaligned record offsets");
+    if (v.nslot != 2 * (v.maxord + 1) + v.nst) return fail(TTM_ERR_ARG, "ttm_plan_create: inconsistent slot count");
+    return TTM_OK;
+}
+
+int ttm_plan_create(ttm_ctx* c, const int32_t* host_iblob, int64_t n_int, const double* host_dblob, int64_t n_double,
+                    ttm_plan** host_out) {
+    if (!c || !host_iblob || !host_dblob || !host_out) return fail(TTM_ERR_ARG, "ttm_plan_create: null argument");
+    CK(cudaSetDevice(c->device));
+    auto* p = new ttm_plan();
+    p->ctx = c;
+    p->n_int = n_int;
+    p->n_double = n_double;
+    CK(cudaMalloc(&p->d_ib, (n_int + 4) * sizeof(int32_t)));
+    CK(cudaMalloc(&p->d_db, (n_double + 4) * sizeof(double)));
+    CK(cudaMemcpy(p->d_ib, host_iblob, n_int * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_db, host_dblob, n_double * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = parse_view(p, host_iblob);
+    if (rc != TTM_OK) { ttm_plan_destroy(p); return rc; }
+    p->m = p->view.m_non + p->view.m_mon;
+    const int m1 = 1 + p->m;
+    CK(cudaMalloc(&p->d_coeffs, (p->m + 1) * sizeof(double)));
+    CK(cudaMalloc(&p->d_out, m1 * sizeof(double)));
+    CK(cudaMalloc(&p->d_partials, (size_t)MAX_GRID * m1 * sizeof(double)));
+    CK(cudaMalloc(&p->d_counter, sizeof(unsigned int)));
+    CK(cudaMemset(p->d_counter, 0, sizeof(unsigned int)));
+    CK(cudaMemset(p->d_coeffs, 0, (p->m + 1) * sizeof(double)));
+    CK(cudaMallocHost(&p->h_pin, 2 * m1 * sizeof(double)));
+    *host_out = p;
+    return TTM_OK;
+}
+
+int ttm_plan_update_doubles(ttm_plan* p, const double* host_dblob, int64_t n_double) {
+    if (!p || !host_dblob || n_double != p->n_double) return fail(TTM_ERR_ARG, "ttm_plan_update_doubles: size mismatch");
+    CK(cudaSetDevice(p->ctx->device));
+    CK(cudaMemcpy(p->d_db, host_dblob, n_double * sizeof(double), cudaMemcpyHostToDevice));
+    return TTM_OK;
+}
+
+int ttm_plan_destroy(ttm_plan* p) {
+    if (!p) return TTM_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->d_ib); cudaFree(p->d_db); cudaFree(p->d_coeffs); cudaFree(p->d_out);
+    cudaFree(p->d_partials); cudaFree(p->d_counter);
+    if (p->h_pin) cudaFreeHost(p->h_pin);
+    delete p;
+    return TTM_OK;
+}
+
+int ttm_colstats(ttm_ctx* c, const double* X, int64_t N, int D, double* mean, double* sd, double* scratch, void* stream) {
+    if (!c || !X || N <= 0 || D <= 0) return fail(TTM_ERR_ARG, "ttm_colstats: bad arguments");
+    CK(cudaSetDevice(c->device));
+    CK(ttm_launch_colstats(X, N, D, mean, sd, scratch, c->sm_count, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_standardize_transpose(ttm_ctx* c, const double* X, int64_t N, int D, const double* mean, const double* sd,
+                              double* Xt, int64_t ld, void* stream) {
+    if (!c || !X || !Xt || N <= 0 || D <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_standardize_transpose: bad arguments");
+    CK(cudaSetDevice(c->device));
+    CK(ttm_launch_standardize_transpose(X, N, D, mean, sd, Xt, ld, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_transpose_back(ttm_ctx* c, const double* Xt, int64_t ld, int64_t N, int D, const double* mean, const double* sd,
+                       double* X, int64_t ldx, void* stream) {
+    if (!c || !X || !Xt || N <= 0 || D <= 0 || ld < N || ldx < D) return fail(TTM_ERR_ARG, "ttm_transpose_back: bad arguments");
+    CK(cudaSetDevice(c->device));
+    CK(ttm_launch_transpose_back(Xt, ld, N, D, mean, sd, X, ldx, 0, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_basis_eval(ttm_plan* p, int which, const double* Xt, int64_t ld, int64_t N, double* Psi, void* stream) {
+    if (!p || !Xt || !Psi || which < 0 || which > 2) return fail(TTM_ERR_ARG, "ttm_basis_eval: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    CK(ttm_launch_basis(p->view, which, Xt, ld, N, Psi, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_plan_set_coeffs(ttm_plan* p, const double* host_coeffs, void* stream) {
+    if (!p || !host_coeffs) return fail(TTM_ERR_ARG, "ttm_plan_set_coeffs: null argument");
+    if (p->m == 0) return TTM_OK;
+    CK(cudaSetDevice(p->ctx->device));
+    std::memcpy(p->h_pin, host_coeffs, p->m * sizeof(double));
+    CK(cudaMemcpyAsync(p->d_coeffs, p->h_pin, p->m * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+static int fill_obj(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, ObjArgs& a) {
+    ttm_ctx* c = p->ctx;
+    if (c->Q <= 0) return fail(TTM_ERR_ARG, "quadrature rule not set (ttm_ctx_set_quadrature)");
+    if (!Xt || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "bad sample matrix");
+    a.P = p->view;
+    a.Xt = Xt; a.ld = ld; a.N = N;
+    a.coeffs = p->d_coeffs;
+    a.xis = c->d_xis; a.ws = c->d_ws; a.Q = c->Q; a.wsum = c->wsum;
+    a.rect = c->rect; a.delta = c->delta;
+    a.partials = p->d_partials; a.counter = p->d_counter; a.out = p->d_out;
+    a.S_out = nullptr;
+    a.max_grid = MAX_GRID;
+    return TTM_OK;
+}
+
+int ttm_objgrad_ir_launch(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, void* stream) {
+    if (!p) return fail(TTM_ERR_ARG, "ttm_objgrad_ir_launch: null plan");
+    CK(cudaSetDevice(p->ctx->device));
+    ObjArgs a;
+    int rc = fill_obj(p, Xt, ld, N, a);
+    if (rc) return rc;
+    cudaError_t e = ttm_launch_objgrad(a, true, p->ctx->sm_count, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_objgrad_ir: component exceeds compiled limits (polynomial order <= 20, <= 8 special inner terms)");
+    CK(e);
+    return TTM_OK;
+}
+
+int ttm_plan_get_out(ttm_plan* p, double* host_out, int n, void* stream) {
+    if (!p || !host_out || n < 0 || n > 1 + p->m) return fail(TTM_ERR_ARG, "ttm_plan_get_out: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    double* pin = p->h_pin + (1 + p->m);
+    CK(cudaMemcpyAsync(pin, p->d_out, n * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    std::memcpy(host_out, pin, n * sizeof(double));
+    return TTM_OK;
+}
+
+int ttm_objgrad_ir(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* host_coeffs, double* host_out,
+                   void* stream) {
+    int rc = ttm_plan_set_coeffs(p, host_coeffs, stream);
+    if (rc) return rc;
+    rc = ttm_objgrad_ir_launch(p, Xt, ld, N, stream);
+    if (rc) return rc;
+    return ttm_plan_get_out(p, host_out, 1 + p->m, stream);
+}
+
+int ttm_eval_s_ir(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, double* S_out, void* stream) {
+    if (!p || !S_out) return fail(TTM_ERR_ARG, "ttm_eval_s_ir: null argument");
+    CK(cudaSetDevice(p->ctx->device));
+    ObjArgs a;
+    int rc = fill_obj(p, Xt, ld, N, a);
+    if (rc) return rc;
+    a.S_out = S_out;
+    cudaError_t e = ttm_launch_objgrad(a, false, p->ctx->sm_count, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_eval_s_ir: component exceeds compiled limits (polynomial order <= 20, <= 8 special inner terms)");
+    CK(e);
+    return TTM_OK;
+}
+
+int ttm_sep_eval(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, double* S_out, const double* Xd, int64_t ldd,
+                 double* dS_out, void* stream) {
+    if (!p || N <= 0 || (S_out && (!Xt || ld < N)) || (dS_out && (!Xd || ldd < N)))
+        return fail(TTM_ERR_ARG, "ttm_sep_eval: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    CK(ttm_launch_sep_eval(p->view, Xt, ld, N, p->d_coeffs, S_out, Xd, ldd, dS_out, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_density_accumulate(ttm_ctx* c, double* acc, const double* S, const double* dS, double sigma, int mode,
+                           int64_t N, void* stream) {
+    if (!c || !acc || !dS || (mode == 0 && !S) || N <= 0) return fail(TTM_ERR_ARG, "ttm_density_accumulate: bad arguments");
+    CK(cudaSetDevice(c->device));
+    CK(ttm_launch_density_acc(acc, S, dS, sigma, mode, N, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_density_finish(ttm_ctx* c, const double* acc, const double* log_target, double* out, int64_t N, void* stream) {
+    if (!c || !acc || !out || N <= 0) return fail(TTM_ERR_ARG, "ttm_density_finish: bad arguments");
+    CK(cudaSetDevice(c->device));
+    CK(ttm_launch_density_finish(acc, log_target, out, N, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_gram(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch, int64_t scratch_doubles,
+             void* stream) {
+    if (!p || !Xt || !G || !scratch || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_gram: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    cudaError_t e = ttm_launch_gram(p->view, Xt, ld, N, G, scratch, scratch_doubles, p->ctx->sm_count, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_gram: scratch too small or too many terms for one shared-memory tile");
+    CK(e);
+    return TTM_OK;
+}
+
+int ttm_sep_objgrad(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* host_b, double* host_out,
+                    void* stream) {
+    if (!p || !Xt || !host_b || !host_out || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    const int mm = p->view.m_dmon;
+    if (mm > p->m) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: inconsistent plan");
+    std::memcpy(p->h_pin, host_b, mm * sizeof(double));
+    double* d_b = p->d_coeffs + p->view.m_non;
+    CK(cudaMemcpyAsync(d_b, p->h_pin, mm * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    cudaError_t e = ttm_launch_sepobj(p->view, Xt, ld, N, d_b, p->ctx->delta, p->d_partials, p->d_counter, p->d_out,
+                                      MAX_GRID, p->ctx->sm_count, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_sep_objgrad: too many monotone terms for shared memory");
+    CK(e);
+    return ttm_plan_get_out(p, host_out, 1 + mm, stream);
+}
+
+int ttm_mon_table(ttm_plan* p, int ntab, double* table, void* stream) {
+    if (!p || !table || ntab < 2) return fail(TTM_ERR_ARG, "ttm_mon_table: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    CK(ttm_launch_mon_table(p->view, p->d_coeffs, ntab, 0, 0, table, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+static void fill_inv(ttm_plan* p, double* Xt, int64_t ld, int64_t N, const double* z, InvArgs& a) {
+    ttm_ctx* c = p->ctx;
+    a.P = p->view;
+    a.Xt = Xt; a.ld = ld; a.N = N; a.z = z;
+    a.coeffs = p->d_coeffs;
+    a.xis = c->d_xis; a.ws = c->d_ws; a.Q = c->Q; a.wsum = c->wsum;
+    a.rect = c->rect; a.delta = c->delta;
+    a.separable = 0;
+    a.table = nullptr; a.ntab = 0; a.truncate = 0;
+    a.first = 0; a.count = N; a.max_iter = 100;
+    a.iter_max = nullptr; a.not_converged = nullptr;
+}
+
+int ttm_inverse_table(ttm_plan* p, double* Xt, int64_t ld, int64_t N, const double* z, const double* table, int ntab,
+                      int truncate, void* stream) {
+    if (!p || !Xt || !z || !table || ntab < 2 || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_inverse_table: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    InvArgs a;
+    fill_inv(p, Xt, ld, N, z, a);
+    a.separable = 1;
+    a.table = table; a.ntab = ntab; a.truncate = truncate;
+    CK(ttm_launch_inverse_table(a, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_inverse_bisect(ttm_plan* p, double* Xt, int64_t ld, int64_t N, const double* z, int separable, int max_iter,
+                       int* host_not_converged, void* stream) {
+    if (!p || !Xt || !z || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_inverse_bisect: bad arguments");
+    ttm_ctx* c = p->ctx;
+    if (!separable && c->Q <= 0) return fail(TTM_ERR_ARG, "quadrature rule not set (ttm_ctx_set_quadrature)");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), st));
+    InvArgs a;
+    fill_inv(p, Xt, ld, N, z, a);
+    a.separable = separable;
+    a.max_iter = max_iter;
+    a.iter_max = c->d_flags;
+    a.not_converged = c->d_flags + 1;
+    // samples 1..N-1 first; sample 0 then iterates only as long as any of them did
+    // (the reference's loop condition sums the remaining *indices*, tm.py:3952)
+    a.first = 1; a.count = N - 1;
+    cudaError_t e = ttm_launch_inverse_bisect(a, st);
+    if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_inverse_bisect: polynomial order > 32 or > 16 special inner terms");
+    CK(e);
+    a.first = 0; a.count = 1;
+    CK(ttm_launch_inverse_bisect(a, st));
+    if (host_not_converged) {
+        CK(cudaMemcpyAsync(host_not_converged, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return TTM_OK;
+}
+
+int ttm_fp64_peak(ttm_ctx* c, double* host_tflops) {
+    if (!c || !host_tflops) return fail(TTM_ERR_ARG, "ttm_fp64_peak: null argument");
+    CK(cudaSetDevice(c->device));
+    double* sink;
+    CK(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int block = 256, grid = c->sm_count * 8, iters = 1 << 16;
+    CK(ttm_launch_fp64_peak(sink, 1024, grid, block, 0));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0, 0));
+        CK(ttm_launch_fp64_peak(sink, iters, grid, block, 0));
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * (double)iters * (double)grid * block / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *host_tflops = best;
+    return TTM_OK;
+}
+
+}  // extern "C"

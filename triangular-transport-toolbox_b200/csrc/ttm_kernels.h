@@ -1,0 +1,89 @@
+// Internal launcher interface between the kernel translation units and the C ABI (ttm_api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ttm_common.cuh"
+
+struct ObjArgs {
+    PlanView P;
+    const double* Xt;      // standardised samples, column-major: column v at Xt + v*ld
+    int64_t ld, N;
+    const double* coeffs;  // device [m_non + m_mon]
+    const double* xis;     // device [Q] Gauss-Legendre nodes
+    const double* ws;      // device [Q] weights
+    int Q;
+    double wsum;           // sum of the weights (host, same summation order as the nodes)
+    int rect;
+    double delta;
+    double* partials;      // device [max_grid][1+m]
+    unsigned int* counter; // device, zero on entry, zero on exit
+    double* out;           // device [1+m]: J, grad
+    double* S_out;         // device [N] (value-only mode)
+    int max_grid;
+};
+
+cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaStream_t st);
+
+// column statistics + standardise + transpose (reference: standardize, transport_map.py:750-787)
+cudaError_t ttm_launch_colstats(const double* X, int64_t N, int D, double* mean, double* std, double* scratch,
+                                int sm_count, cudaStream_t st);
+cudaError_t ttm_launch_standardize_transpose(const double* X, int64_t N, int D, const double* mean,
+                                             const double* std, double* Xt, int64_t ld, cudaStream_t st);
+cudaError_t ttm_launch_transpose_back(const double* Xt, int64_t ld, int64_t N, int D, const double* mean,
+                                      const double* std, double* X, int64_t ldx, int col0, cudaStream_t st);
+
+// basis matrices (reference: generated fun_mon_k / fun_nonmon_k / der_fun_mon_k + precalculate :789-821)
+cudaError_t ttm_launch_basis(const PlanView& P, int which, const double* Xt, int64_t ld, int64_t N, double* Psi,
+                             cudaStream_t st);
+
+// separable-monotonicity evaluation: S_k and d_k S_k per sample (reference: s :2550-2558, densities :2620-2641)
+cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* coeffs,
+                                double* S_out, const double* Xd, int64_t ldd, double* dS_out, cudaStream_t st);
+
+cudaError_t ttm_launch_density_acc(double* acc, const double* S, const double* dS, double sigma, int mode, int64_t N,
+                                   cudaStream_t st);
+cudaError_t ttm_launch_density_finish(const double* acc, const double* logt, double* out, int64_t N, cudaStream_t st);
+
+// Gram matrix of [Psi_non | Psi_mon] (reference: worker_task_monotone :2966-2975, :3031-3050)
+cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch,
+                            int64_t scratch_doubles, int sm_count, cudaStream_t st);
+
+// reduced separable objective: sum log dS, colsum(dPsi/dS) (reference: fun_mon_objective :2978-3018)
+cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* b,
+                              double delta, double* partials, unsigned int* counter, double* out, int max_grid,
+                              int sm_count, cudaStream_t st);
+
+struct InvArgs {
+    PlanView P;
+    double* Xt;            // working sample matrix (columns < c already solved); column c is written
+    int64_t ld, N;
+    const double* z;       // device [N] target values of this component
+    const double* coeffs;  // device [m_non + m_mon]
+    // integrated rectifier
+    const double* xis;
+    const double* ws;
+    int Q;
+    double wsum;
+    int rect;
+    double delta;
+    int separable;
+    // table mode
+    const double* table;   // device [ntab] sorted monotone-part values, abscissae in table + ntab
+    int ntab;
+    int truncate;
+    // bisection quirk bookkeeping (transport_map.py:3952): iterations used by samples >= 1
+    int64_t first, count;  // sample range handled by this launch
+    int max_iter;
+    int* iter_max;         // device scalar
+    int* not_converged;    // device counter of samples stopped at max_iter
+};
+
+cudaError_t ttm_launch_inverse_table(const InvArgs& a, cudaStream_t st);
+cudaError_t ttm_launch_inverse_bisect(const InvArgs& a, cudaStream_t st);
+cudaError_t ttm_launch_mon_table(const PlanView& P, const double* coeffs, int ntab, double lo, double hi,
+                                 double* table, cudaStream_t st);
+
+// FP64 pipe micro-benchmark (dependent-free DFMA chains); returns flop count per launch
+cudaError_t ttm_launch_fp64_peak(double* sink, int iters, int grid, int block, cudaStream_t st);

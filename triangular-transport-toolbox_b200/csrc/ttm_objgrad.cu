@@ -1,0 +1,37 @@
+// Dispatcher of K-objgrad / K-S: picks the narrowest compiled instantiation that covers the
+// component's slot structure (see ttm_objgrad_impl.cuh for the kernel).
+#include "ttm_objgrad_impl.cuh"
+
+// Returns cudaErrorInvalidValue if the plan exceeds the compiled limits (order > 20 or > 8
+// special-term inner factors).
+cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaStream_t st) {
+    using ttm_obj::T_OBJ;
+    const PlanView& P = a.P;
+    const int m = P.m_non + P.m_mon;
+    const bool herme = (P.family == FAM_HERMITE_E);
+    const bool exprect = (a.rect == RECT_EXP);
+    const int64_t rows = (a.N + T_OBJ - 1) / T_OBJ;
+    const int nslot_rt = 2 * (P.maxord + 1) + P.nst;
+    auto smem_for = [&](int maxord_t) {
+        return sizeof(double) * (size_t)(m + 2 * a.Q + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0));
+    };
+    auto grid_for = [&](int blocks_per_sm) {
+        int64_t g = (int64_t)sm_count * blocks_per_sm;
+        if (g > rows) g = rows;
+        if (g > a.max_grid) g = a.max_grid;
+        return (int)(g < 1 ? 1 : g);
+    };
+    if (P.nst == 0 && herme && exprect && !P.has_plain && P.maxord <= 3)
+        return ttm_objgrad_cfg0(a, grad, grid_for(4), smem_for(3), st);
+    if (P.nst == 0 && herme && exprect && P.maxord <= 3)
+        return ttm_objgrad_cfg1(a, grad, grid_for(4), smem_for(3), st);
+    if (P.nst == 0 && herme && exprect && P.maxord <= 6)
+        return ttm_objgrad_cfg2(a, grad, grid_for(3), smem_for(6), st);
+    if (P.nst == 0 && herme && exprect && P.maxord <= 12)
+        return ttm_objgrad_cfg3(a, grad, grid_for(3), smem_for(12), st);
+    if (P.nst == 0 && P.maxord <= 6)
+        return ttm_objgrad_cfg4(a, grad, grid_for(3), smem_for(6), st);
+    if (P.nst <= 8 && P.maxord <= 20)
+        return ttm_objgrad_cfg5(a, grad, grid_for(2), smem_for(20), st);
+    return cudaErrorInvalidValue;
+}

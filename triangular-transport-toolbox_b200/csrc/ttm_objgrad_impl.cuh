@@ -1,0 +1,361 @@
+// K-objgrad / K-S (integrated rectifier): fused objective + gradient of one map component.
+//
+// Replaces, in ONE launch, the reference's three quadrature sweeps per optimizer callback pair:
+//   objective_function            transport_map.py:3300-3433
+//   objective_function_jacobian   transport_map.py:3435-3635
+//   s (integrated-rectifier arm)  transport_map.py:2439-2547
+//   GaussQuadrature vector branch transport_map.py:4202-4278
+//   rectifier                     transport_map.py:4956-5213
+//
+// Work decomposition per thread block (T threads) over a contiguous range of sample rows:
+//   phase A  S_non[r]  = sum_j a_j psi^non_j(x_<c)      -- variable-major sweep, R samples/thread
+//   phase B  node loop: M = int_0^{x_c} g(sum_j b_j psi^mon_j) dt, I_s = int g' phi_s dt per *slot*
+//            (slot = distinct univariate factor of x_c; outer factors u_j(x_<c) are folded into the
+//            slot coefficients C_s = sum_j b_j u_j, so the loop body is independent of m_mon)
+//   phase C  dJ/da_j   = sum_i S_i psi^non_j(x_i)        -- same sweep as A, warp-reduced per term
+// Block partials go to a [grid][1+m] buffer; the last block to finish reduces them in fixed
+// block order (bit-reproducible), divides by N and writes (J, grad) to `out`.
+//
+// Bound: FP64 pipe (two exp per quadrature node), not HBM: algorithmic bytes 8*N*(c+1).
+//
+// This header is included by one translation unit per instantiation (ttm_objgrad_cfg*.cu) so the
+// variants compile in parallel.
+#pragma once
+
+#include "ttm_common.cuh"
+#include "ttm_kernels.h"
+#include "ttm_sweep.cuh"
+
+namespace ttm_obj {
+
+constexpr int T_OBJ = 128;  // threads per block
+
+// ---- polynomial ladder on the inner variable: fills P[0..MAXORD] ----
+template <int MAXORD, bool HERME>
+__device__ __forceinline__ void ladder(double t, const double* __restrict__ rec, double (&P)[MAXORD + 1]) {
+    P[0] = 1.0;
+    if (HERME) {
+        if (MAXORD >= 1) P[1] = t;
+#pragma unroll
+        for (int n = 1; n < MAXORD; ++n) P[n + 1] = fma(t, P[n], -(double)n * P[n - 1]);
+    } else {
+        if (MAXORD >= 1) P[1] = fma(rec[0], t, rec[MAXORD + 1]);
+#pragma unroll
+        for (int n = 1; n < MAXORD; ++n)
+            P[n + 1] = fma(fma(rec[n], t, rec[MAXORD + 1 + n]), P[n], -rec[2 * (MAXORD + 1) + n] * P[n - 1]);
+    }
+}
+
+// outer (x_<c) product of monotone term j on sample i; 1 if the term has no outer factor
+static __device__ __noinline__ double outer_product(const PlanView& P, int j, const double* __restrict__ Xt,
+                                                    int64_t ld, int64_t i) {
+    const int b = __ldg(P.ib + P.o_out_ptr + j), e = __ldg(P.ib + P.o_out_ptr + j + 1);
+    double v = 1.0;
+    for (int q = b; q < e; ++q) v *= plan_factor(P, __ldg(P.ib + P.o_out_fac + q), Xt, ld, i);
+    return v;
+}
+
+template <int MAXORD, bool HAS_PLAIN, bool HAS_HF, int NST, bool HERME, bool EXPRECT, bool GRAD, int RB>
+__global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
+    extern __shared__ double smem[];
+    const PlanView& P = a.P;
+    const int m = P.m_non + P.m_mon;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = T_OBJ / 32;
+    constexpr int NSLOT_T = 2 * (MAXORD + 1) + NST;       // slots of this instantiation
+    constexpr int NSTA = NST > 0 ? NST : 1;
+    const int st_base = 2 * (P.maxord + 1);               // first special-term slot of the plan
+    const int nslot_rt = st_base + P.nst;
+
+    double* s_coef = smem;
+    double* s_xis = s_coef + m;
+    double* s_ws = s_xis + a.Q;
+    double* s_rec = s_ws + a.Q;
+    double* s_scale = s_rec + 3 * (MAXORD + 1);
+    double* s_gacc = s_scale + nslot_rt;
+
+    for (int j = tid; j < m; j += T_OBJ) s_coef[j] = a.coeffs[j];
+    for (int q = tid; q < a.Q; q += T_OBJ) {
+        s_xis[q] = a.xis[q];
+        s_ws[q] = a.ws[q];
+    }
+    for (int n = tid; n < 3 * (MAXORD + 1); n += T_OBJ) {
+        double A, B, C;
+        rec_coef(P.family, n % (MAXORD + 1), A, B, C);
+        s_rec[n] = (n / (MAXORD + 1) == 0) ? A : ((n / (MAXORD + 1) == 1) ? B : C);
+    }
+    for (int s = tid; s < nslot_rt; s += T_OBJ) s_scale[s] = P.db[P.o_d_slot_scale + s];
+    if (GRAD)
+        for (int j = tid; j < NW * (1 + m); j += T_OBJ) s_gacc[j] = 0.0;
+    __syncthreads();
+
+    const double* acoef = s_coef;
+    const double* bcoef = s_coef + P.m_non;
+    double* gslot = s_gacc + warp * (1 + m) + 1;  // gradient slots of this warp (slot -1 = J)
+    const double* __restrict__ Xt = a.Xt;
+    const int64_t ld = a.ld, N = a.N;
+    const double* xc_col = Xt + (int64_t)P.c * ld;
+
+    // special-term inner factors (generic instantiation only)
+    int4 sti[NSTA];
+    double4 std_[NSTA];
+    if (NST > 0) {
+#pragma unroll
+        for (int q = 0; q < NST; ++q) {
+            sti[q] = make_int4(0, F_ZERO, 0, 0);
+            std_[q] = make_double4(0, 0, 0, 1);
+            if (q < P.nst) {
+                const int f = __ldg(P.ib + P.o_st_fac + q);
+                sti[q] = __ldg(reinterpret_cast<const int4*>(P.ib + P.o_fac_i) + f);
+                std_[q] = ldg_d4(reinterpret_cast<const double4*>(P.db + P.o_d_fac) + f);
+            }
+        }
+    }
+
+    double Jacc = 0.0;
+    const int64_t rows = (N + T_OBJ - 1) / T_OBJ;
+    const int64_t row_lo = rows * blockIdx.x / gridDim.x, row_hi = rows * (blockIdx.x + 1) / gridDim.x;
+
+    for (int64_t row0 = row_lo; row0 < row_hi; row0 += R_OBJ) {
+        int64_t idx[R_OBJ];
+        double valid[R_OBJ], S[R_OBJ];
+#pragma unroll
+        for (int r = 0; r < R_OBJ; ++r) {
+            const int64_t i = (row0 + r) * T_OBJ + tid;
+            const bool ok = (row0 + r < row_hi) && (i < N);
+            valid[r] = ok ? 1.0 : 0.0;
+            idx[r] = ok ? i : (N - 1);
+            S[r] = 0.0;
+        }
+        // ---------------- phase A ----------------
+        nonmon_sweep<false>(P, Xt, ld, idx, acoef, S, gslot, lane);
+
+        // ---------------- phase B ----------------
+#pragma unroll 1
+        for (int r0 = 0; r0 < R_OBJ; r0 += RB) {
+            double hx[RB], xc[RB], Sacc[RB];
+            double Cp[MAXORD + 1][RB], Ch[MAXORD + 1][RB], Cs[NSTA][RB];
+            double Ip[MAXORD + 1][RB], Ih[MAXORD + 1][RB], Is[NSTA][RB];
+            double tmp[RB][NSLOT_T];  // staging between the rolled (per plan slot) and unrolled code
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                xc[rb] = xc_col[idx[r0 + rb]];
+                hx[rb] = 0.5 * xc[rb];
+                Sacc[rb] = 0.0;
+#pragma unroll
+                for (int s = 0; s < NSLOT_T; ++s) tmp[rb][s] = 0.0;
+            }
+            // slot coefficients C_s = scale_s * sum_{j in s} b_j u_j   (rolled over the plan's slots)
+#pragma unroll 1
+            for (int s = 0; s < nslot_rt; ++s) {
+                const int j0 = __ldg(P.ib + P.o_slot_ptr + s), j1 = __ldg(P.ib + P.o_slot_ptr + s + 1);
+                if (j0 == j1) continue;
+                const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
+                double acc[RB];
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) acc[rb] = 0.0;
+                for (int jj = j0; jj < j1; ++jj) {
+                    const int j = __ldg(P.ib + P.o_slot_term + jj);
+                    const double b = bcoef[j];
+                    const bool has_outer = __ldg(P.ib + P.o_out_ptr + j) != __ldg(P.ib + P.o_out_ptr + j + 1);
+#pragma unroll
+                    for (int rb = 0; rb < RB; ++rb)
+                        acc[rb] = fma(b, has_outer ? outer_product(P, j, Xt, ld, idx[r0 + rb]) : 1.0, acc[rb]);
+                }
+                const double sc = s_scale[s];
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) tmp[rb][ts] = acc[rb] * sc;
+            }
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+#pragma unroll
+                for (int o = 0; o <= MAXORD; ++o) {
+                    Cp[o][rb] = tmp[rb][2 * o]; Ip[o][rb] = 0.0;
+                    Ch[o][rb] = tmp[rb][2 * o + 1]; Ih[o][rb] = 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < NST; ++q) { Cs[q][rb] = tmp[rb][2 * (MAXORD + 1) + q]; Is[q][rb] = 0.0; }
+            }
+
+            // r(t) and the slot basis values at t for sample rb
+            auto inner = [&](int rb, double t, double (&Pl)[MAXORD + 1], double& ga, double (&sv)[NSTA]) {
+                ladder<MAXORD, HERME>(t, s_rec, Pl);
+                double r = 0.0;
+                if (HAS_HF) {
+                    ga = exp(-0.25 * t * t);
+                    double u = 0.0;
+#pragma unroll
+                    for (int o = 1; o <= MAXORD; ++o) u = fma(Ch[o][rb], Pl[o], u);
+                    r = ga * u;
+                }
+                if (HAS_PLAIN) {
+#pragma unroll
+                    for (int o = 0; o <= MAXORD; ++o) r = fma(Cp[o][rb], Pl[o], r);
+                }
+                if (NST > 0) {
+#pragma unroll 1
+                    for (int q = 0; q < NST; ++q) {
+                        sv[q] = (q < P.nst) ? eval_factor(sti[q].y, sti[q].z, std_[q].x, std_[q].y, std_[q].z, std_[q].w, P.family, t) : 0.0;
+                        r = fma(Cs[q][rb], sv[q], r);
+                    }
+                }
+                return r;
+            };
+
+            // ---- Gauss-Legendre node loop (transport_map.py:4252-4278) ----
+#pragma unroll 1
+            for (int q = 0; q < a.Q; ++q) {
+                const double xi = s_xis[q], w = s_ws[q];
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) {
+                    const double t = fma(hx[rb], xi, hx[rb]);
+                    double Pl[MAXORD + 1], ga = 1.0, sv[NSTA];
+                    const double r = inner(rb, t, Pl, ga, sv);
+                    const double g = EXPRECT ? exp(r) : rect_eval(a.rect, r);
+                    Sacc[rb] = fma(w, g, Sacc[rb]);
+                    if (GRAD) {
+                        const double wd = w * (EXPRECT ? g : rect_dfac(a.rect, r, g));
+                        if (HAS_PLAIN) {
+#pragma unroll
+                            for (int o = 0; o <= MAXORD; ++o) Ip[o][rb] = fma(wd, Pl[o], Ip[o][rb]);
+                        }
+                        if (HAS_HF) {
+                            const double wg = wd * ga;
+#pragma unroll
+                            for (int o = 1; o <= MAXORD; ++o) Ih[o][rb] = fma(wg, Pl[o], Ih[o][rb]);
+                        }
+                        if (NST > 0) {
+#pragma unroll
+                            for (int qq = 0; qq < NST; ++qq) Is[qq][rb] = fma(wd, sv[qq], Is[qq][rb]);
+                        }
+                    }
+                }
+            }
+
+            // ---- per-sample epilogue ----
+            double Sfull[RB], ratio[RB];
+            double base[RB][NSLOT_T];   // slot basis values at x_c (local memory, indexed by plan slot below)
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                const double M = hx[rb] * fma(a.delta, a.wsum, Sacc[rb]);  // sum_q hx w_q (g_q + delta)
+                Sfull[rb] = S[r0 + rb] + M;
+                if (GRAD) {
+                    double Plx[MAXORD + 1], gax = 1.0, svx[NSTA];
+                    const double rc = inner(rb, xc[rb], Plx, gax, svx);
+                    const double gc = EXPRECT ? exp(rc) : rect_eval(a.rect, rc);
+                    const double L = rect_log(a.rect, rc, gc, a.delta);
+                    ratio[rb] = (EXPRECT ? gc : rect_dfac(a.rect, rc, gc)) / (gc + a.delta);
+                    Jacc += valid[r0 + rb] * (0.5 * Sfull[rb] * Sfull[rb] - L);
+                    S[r0 + rb] = valid[r0 + rb] * Sfull[rb];
+#pragma unroll
+                    for (int o = 0; o <= MAXORD; ++o) {
+                        tmp[rb][2 * o] = HAS_PLAIN ? Ip[o][rb] : 0.0;
+                        tmp[rb][2 * o + 1] = (HAS_HF && o > 0) ? Ih[o][rb] : 0.0;
+                        base[rb][2 * o] = Plx[o];
+                        base[rb][2 * o + 1] = Plx[o] * gax;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NST; ++q) {
+                        tmp[rb][2 * (MAXORD + 1) + q] = Is[q][rb];
+                        base[rb][2 * (MAXORD + 1) + q] = svx[q];
+                    }
+                } else {
+                    S[r0 + rb] = Sfull[rb];
+                }
+            }
+            if (GRAD) {
+                // dJ/db_j = sum_i u_ij [ S_i hx_i I_{i,s} - ratio_i phi_s(x_ic) ],  s = slot of term j
+#pragma unroll 1
+                for (int s = 0; s < nslot_rt; ++s) {
+                    const int j0 = __ldg(P.ib + P.o_slot_ptr + s), j1 = __ldg(P.ib + P.o_slot_ptr + s + 1);
+                    if (j0 == j1) continue;
+                    const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
+                    const double sc = s_scale[s];
+                    double W[RB];
+#pragma unroll
+                    for (int rb = 0; rb < RB; ++rb)
+                        W[rb] = valid[r0 + rb] * sc * (Sfull[rb] * hx[rb] * tmp[rb][ts] - ratio[rb] * base[rb][ts]);
+                    for (int jj = j0; jj < j1; ++jj) {
+                        const int j = __ldg(P.ib + P.o_slot_term + jj);
+                        const bool has_outer = __ldg(P.ib + P.o_out_ptr + j) != __ldg(P.ib + P.o_out_ptr + j + 1);
+                        double v = 0.0;
+#pragma unroll
+                        for (int rb = 0; rb < RB; ++rb)
+                            v = fma(has_outer ? outer_product(P, j, Xt, ld, idx[r0 + rb]) : 1.0, W[rb], v);
+                        v = warp_sum(v);
+                        if (lane == 0) gslot[P.m_non + j] += v;
+                    }
+                }
+            }
+        }
+
+        if (!GRAD) {
+#pragma unroll
+            for (int r = 0; r < R_OBJ; ++r)
+                if (valid[r] != 0.0) a.S_out[idx[r]] = S[r];
+        } else {
+            // ---------------- phase C ----------------
+            nonmon_sweep<true>(P, Xt, ld, idx, acoef, S, gslot, lane);
+        }
+    }
+
+    if (!GRAD) return;
+
+    // ---- block partial -> global; last block reduces over blocks in fixed order ----
+    Jacc = warp_sum(Jacc);
+    if (lane == 0) gslot[-1] = Jacc;
+    __syncthreads();
+    double* part = a.partials + (int64_t)blockIdx.x * (1 + m);
+    for (int j = tid; j < 1 + m; j += T_OBJ) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += s_gacc[w * (1 + m) + j];
+        part[j] = v;
+    }
+    __threadfence();
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const double invN = 1.0 / (double)N;
+        for (int j = tid; j < 1 + m; j += T_OBJ) {
+            double v = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(a.partials + (int64_t)b * (1 + m) + j);
+            a.out[j] = v * invN;
+        }
+        if (tid == 0) *a.counter = 0u;
+    }
+}
+
+template <int MAXORD, bool HAS_PLAIN, bool HAS_HF, int NST, bool HERME, bool EXPRECT, int RB>
+cudaError_t launch_cfg(const ObjArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e;
+    if (grad) {
+        auto k = objgrad_kernel<MAXORD, HAS_PLAIN, HAS_HF, NST, HERME, EXPRECT, true, RB>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, T_OBJ, smem, st>>>(a);
+    } else {
+        auto k = objgrad_kernel<MAXORD, HAS_PLAIN, HAS_HF, NST, HERME, EXPRECT, false, RB>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, T_OBJ, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace ttm_obj
+
+// one exported launcher per instantiation (defined in ttm_objgrad_cfg<N>.cu)
+#define TTM_OBJ_CFG_LIST(X)                          \
+    X(0, 3, false, true, 0, true, true, 2)           \
+    X(1, 3, true, true, 0, true, true, 2)            \
+    X(2, 6, true, true, 0, true, true, 2)            \
+    X(3, 12, true, true, 0, true, true, 1)           \
+    X(4, 6, true, true, 0, false, false, 2)          \
+    X(5, 20, true, true, 8, false, false, 1)
+
+#define TTM_OBJ_DECL(ID, MAXORD, HP, HH, NST, HERME, EXPR, RB) \
+    cudaError_t ttm_objgrad_cfg##ID(const ObjArgs& a, bool grad, int grid, size_t smem, cudaStream_t st);
+TTM_OBJ_CFG_LIST(TTM_OBJ_DECL)
+#undef TTM_OBJ_DECL

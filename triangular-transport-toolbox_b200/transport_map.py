@@ -1,0 +1,764 @@
+"""
+`transport_map` -- drop-in class for the hot path of the Triangular Transport Toolbox, backed by
+hand-written sm_100a CUDA kernels behind the C ABI of libttm.so (include/ttm.h).
+
+Mirrors the reference class (`/root/reference/transport_map.py`, "tm.py"): constructor signature and
+defaults tm.py:12-39, public attributes, `optimize`, `map`, `inverse_map`, `reset`, `s`,
+`objective_function`, `objective_function_jacobian`, `evaluate_pullback_density`,
+`evaluate_pushforward_density`.  What stays on the host is what the reference's callers own: the
+scipy optimizer steps (BFGS / L-BFGS-B, tm.py:3252-3257 / :3108-3114), the m x m linear algebra of
+the separable fit, quantile look-ups for special-term placement, and option/error handling.
+
+Out of scope: map adaptation (`adapt_map`), adaptive quadrature order, the
+generated-source strings (`fun_mon_strings` ...), `projectedNewton`, progress bars.
+
+PyTorch is used for device buffers, streams and (multi-GPU) torch.distributed only.
+"""
+
+import copy
+
+import numpy as np
+
+from . import binding as B
+from .plan import ComponentPlan, resolve_family
+
+_RECT = {'exponential': 0, 'softplus': 1, 'squared': 2, 'expneg': 3, 'explinearunit': 4}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise B.TTMError('no CUDA device visible: this package runs on B200 (sm_100a) only and has no CPU fallback')
+    return torch
+
+
+class _LazyList:
+    """List-like view whose items are computed on first access (Psi_mon, Psi_nonmon, der_Psi_mon)."""
+
+    def __init__(self, n, compute):
+        self._n, self._compute, self._cache = n, compute, {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(self._n))]
+        k = int(k)
+        if k < 0:
+            k += self._n
+        if not 0 <= k < self._n:
+            raise IndexError(k)
+        if k not in self._cache:
+            self._cache[k] = self._compute(k)
+        return self._cache[k]
+
+    def __setitem__(self, k, v):
+        self._cache[int(k)] = v
+
+    def __iter__(self):
+        return (self[k] for k in range(self._n))
+
+
+class transport_map():
+
+    def __init__(self,
+                 X,
+                 monotone=None,
+                 nonmonotone=None,
+                 polynomial_type='hermite function',
+                 monotonicity='integrated rectifier',
+                 standardize_samples=True,
+                 standardization='standard',
+                 workers=1,
+                 ST_scale_factor=1.0,
+                 ST_scale_mode='dynamic',
+                 coeffs_init=0.,
+                 alternate_root_finding=True,
+                 root_search_truncation=True,
+                 verbose=True,
+                 linearization=None,
+                 linearization_specified_as_quantiles=True,
+                 linearization_increment=1E-6,
+                 regularization=None,
+                 regularization_lambda=0.1,
+                 quadrature_input={},
+                 rectifier_type='exponential',
+                 delta=1E-8,
+                 adaptation=False,
+                 adaptation_map_type="cross-terms",
+                 adaptation_max_order=10,
+                 adaptation_skip_dimensions=0,
+                 adaptation_max_iterations=25,
+                 device=None):
+        """Same arguments as the reference constructor (tm.py:12-168).  `device` (extra, optional)
+        selects the CUDA device index; default: torch's current device."""
+        torch = _torch()
+        self._torch = torch
+        self._dev_index = torch.cuda.current_device() if device is None else int(device)
+        self._device = torch.device('cuda', self._dev_index)
+        self._lib = B.lib()
+
+        self.monotone = copy.deepcopy(monotone)
+        self.nonmonotone = copy.deepcopy(nonmonotone)
+        self.workers = workers
+        self.rectifier_type = rectifier_type
+        self.delta = delta
+        if rectifier_type not in _RECT:
+            raise ValueError("rectifier_type " + str(rectifier_type) + " not understood.")
+
+        # Gauss-Legendre rule, computed exactly as tm.py:199-225 (legroots + closed-form weights)
+        self.quadrature_input = quadrature_input
+        if 'xis' not in self.quadrature_input and 'Ws' not in self.quadrature_input:
+            order = self.quadrature_input.get('order', 100)
+            coefs = [0] * order + [1]
+            LegendreDer = np.polynomial.legendre.Legendre(np.polynomial.legendre.legder(coefs))
+            xis = np.polynomial.legendre.legroots(coefs)
+            Ws = 2.0 / ((1.0 - xis ** 2) * (LegendreDer(xis) ** 2))
+            self.quadrature_input['xis'] = copy.copy(xis)
+            self.quadrature_input['Ws'] = copy.copy(Ws)
+        if self.quadrature_input.get('adaptive', False):
+            raise NotImplementedError("adaptive quadrature order is out of scope of the CUDA path (SURVEY.md section 2)")
+
+        self.ST_scale_factor = ST_scale_factor
+        self.ST_scale_mode = ST_scale_mode
+        if self.ST_scale_mode not in ['dynamic', 'static']:
+            raise ValueError("'ST_scale_mode' must be either 'dynamic' or 'static'.")
+        self.standardization = standardization
+        self.coeffs_init = coeffs_init
+        self.alternate_root_finding = alternate_root_finding
+        self.root_search_truncation = root_search_truncation
+        self.verbose = verbose
+        self.regularization = regularization
+        self.regularization_lambda = regularization_lambda
+        self.linearization = linearization
+        self.linearization_specified_as_quantiles = linearization_specified_as_quantiles
+        self.linearization_increment = linearization_increment
+        self.monotonicity = monotonicity
+        if self.monotonicity.lower() not in ['integrated rectifier', 'separable monotonicity']:
+            raise ValueError("'monotonicity' type " + str(self.monotonicity) + " not understood. " +
+                             "Must be either 'integrated rectifier' or 'separable monotonicity'.")
+        self._family, self.polyfunc, self.polyfunc_der, self.polynomial_type = resolve_family(polynomial_type)
+        self.polyfunc_str = "np.polynomial." + self.polyfunc.__name__
+
+        self.adaptation = adaptation
+        if adaptation:
+            raise NotImplementedError("map adaptation is out of scope of the CUDA path (SURVEY.md section 2)")
+        self.adaptation_map_type = adaptation_map_type.lower()
+        self.adaptation_max_order = adaptation_max_order
+        self.adaptation_skip_dimensions = adaptation_skip_dimensions
+        self.adaptation_max_iterations = adaptation_max_iterations
+
+        # ---- device context
+        ctx = B.c_void_p()
+        B.check(self._lib.ttm_ctx_create(self._dev_index, B.ctypes.byref(ctx)))
+        self._ctx = ctx
+        xis = np.ascontiguousarray(self.quadrature_input['xis'], dtype=np.float64)
+        Ws = np.ascontiguousarray(self.quadrature_input['Ws'], dtype=np.float64)
+        B.check(self._lib.ttm_ctx_set_quadrature(ctx, B.dptr(xis), B.dptr(Ws), len(xis)))
+        B.check(self._lib.ttm_ctx_set_rectifier(ctx, _RECT[rectifier_type], float(delta)))
+        sm = B.c_int()
+        B.check(self._lib.ttm_device_sm_count(self._dev_index, B.ctypes.byref(sm)))
+        self._sm_count = sm.value
+        self._scratch = torch.empty(max(4 * self._sm_count * 256, 1 << 16), dtype=torch.float64, device=self._device)
+
+        # ---- samples (tm.py:311-314, 327-328)
+        self.standardize_samples = standardize_samples
+        self.D = len(monotone)
+        self.skip_dimensions = X.shape[-1] - self.D
+        self._plans = None
+        self._load_samples(X)
+
+        # ---- term tables (replaces function_constructor_alternative, tm.py:358)
+        self.check_for_special_terms()
+        self.determine_special_term_locations()
+        self._compile_plans()
+        self.coeffs_mon = [np.ones(p.m_mon) * self.coeffs_init for p in self._host_plans]
+        self.coeffs_nonmon = [np.ones(len(self.nonmonotone[k])) * self.coeffs_init for k in range(self.D)]
+        if self.monotonicity.lower() == 'separable monotonicity':
+            self.optimization_constraints_lb = [p.lb.copy() for p in self._host_plans]
+            self.optimization_constraints_ub = [p.ub.copy() for p in self._host_plans]
+        self._make_callables()
+        self.precalculate()
+
+    # ================================================================== plumbing
+    def _stream(self):
+        return B.c_void_p(self._torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _empty(self, *shape):
+        return self._torch.empty(*shape, dtype=self._torch.float64, device=self._device)
+
+    def _upload(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return self._torch.from_numpy(a).to(self._device, non_blocking=False)
+
+    def _to_colmajor(self, X_host, mean=None, std=None):
+        """row-major host (n, d) -> device column-major (d, n), optionally standardised with (mean, std)."""
+        n, d = X_host.shape
+        Xd = self._upload(X_host)
+        Xt = self._empty(d, n)
+        mp = B.c_void_p(mean.data_ptr()) if mean is not None else None
+        sp = B.c_void_p(std.data_ptr()) if std is not None else None
+        B.check(self._lib.ttm_standardize_transpose(self._ctx, B.c_void_p(Xd.data_ptr()), n, d, mp, sp,
+                                                    B.c_void_p(Xt.data_ptr()), n, self._stream()))
+        return Xt
+
+    def _to_rowmajor(self, Xt, n, d, mean=None, std=None):
+        """device column-major (d, ld>=n) -> host row-major (n, d), optionally un-standardised."""
+        out = self._empty(n, d)
+        mp = B.c_void_p(mean.data_ptr()) if mean is not None else None
+        sp = B.c_void_p(std.data_ptr()) if std is not None else None
+        B.check(self._lib.ttm_transpose_back(self._ctx, B.c_void_p(Xt.data_ptr()), Xt.shape[1], n, d, mp, sp,
+                                             B.c_void_p(out.data_ptr()), d, self._stream()))
+        return out.cpu().numpy()
+
+    def _load_samples(self, X):
+        """Upload the training ensemble, standardise it on the device (tm.py:750-787) and keep the
+        column-major copy resident."""
+        torch = self._torch
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise Exception('X should be a two-dimensional array of shape (N,D), N = number of samples, '
+                            'D = number of dimensions. Current shape of X is ' + str(X.shape))
+        n, d = X.shape
+        self._N, self._Dtot = n, d
+        self._X_host = None
+        if not self.standardize_samples:
+            self._Xt = self._to_colmajor(X)
+            self._mean_d = self._std_d = None
+            return
+        mode = self.standardization.lower()
+        if mode == 'standard':
+            Xd = self._upload(X)
+            self._mean_d, self._std_d = self._empty(d), self._empty(d)
+            B.check(self._lib.ttm_colstats(self._ctx, B.c_void_p(Xd.data_ptr()), n, d,
+                                           B.c_void_p(self._mean_d.data_ptr()), B.c_void_p(self._std_d.data_ptr()),
+                                           B.c_void_p(self._scratch.data_ptr()), self._stream()))
+            self._Xt = self._empty(d, n)
+            B.check(self._lib.ttm_standardize_transpose(self._ctx, B.c_void_p(Xd.data_ptr()), n, d,
+                                                        B.c_void_p(self._mean_d.data_ptr()),
+                                                        B.c_void_p(self._std_d.data_ptr()),
+                                                        B.c_void_p(self._Xt.data_ptr()), n, self._stream()))
+            self.X_mean = self._mean_d.cpu().numpy()
+            self.X_std = self._std_d.cpu().numpy()
+            del Xd
+        elif mode in ('quantile', 'quantiles'):
+            # order statistics: host numpy (setup, not hot), exactly tm.py:775-778
+            self.X_mean = np.quantile(X, q=0.5, axis=0)
+            self.X_std = (np.quantile(X - self.X_mean, q=0.8413447460685429, axis=0) -
+                          np.quantile(X - self.X_mean, q=0.15865525393145707, axis=0)) / 2
+            self._mean_d, self._std_d = self._upload(self.X_mean), self._upload(self.X_std)
+            self._Xt = self._to_colmajor(X, self._mean_d, self._std_d)
+        else:
+            raise ValueError("'standardization' must be either 'standard' or 'quantiles'.")
+        torch.cuda.current_stream(self._device).synchronize()
+
+    @property
+    def X(self):
+        """Standardised training samples (N, Dtot), downloaded on demand (the resident copy is column-major)."""
+        if self._X_host is None:
+            self._X_host = np.ascontiguousarray(self._Xt.cpu().numpy().T)
+        return self._X_host
+
+    @X.setter
+    def X(self, value):
+        value = np.asarray(value, dtype=np.float64)
+        self._Xt = self._to_colmajor(value)
+        self._N, self._Dtot = value.shape
+        self._X_host = None
+
+    def _column(self, d):
+        return self._Xt[d].cpu().numpy()
+
+    # ================================================================== special terms
+    def check_for_special_terms(self):
+        """Counts RBF-type terms per (component, variable); tm.py:2136-2217."""
+        blank = lambda: {'counter': 0, 'centers': np.asarray([]), 'scales': np.asarray([])}
+        self.special_terms = {}
+        for k in range(self.D):
+            c = k + self.skip_dimensions
+            st = self.special_terms[c] = {}
+            for entry in self.nonmonotone[k]:
+                if type(entry) == str:
+                    st.setdefault(int(entry.split(' ')[1]), blank())['counter'] += 1
+            for entry in self.monotone[k]:
+                if type(entry) == str:
+                    idx = int(entry.split(' ')[1])
+                    if idx == c:
+                        st.setdefault(idx, blank())['counter'] += 1
+                    else:
+                        st.setdefault('cross-terms', {}).setdefault(idx, blank())['counter'] += 1
+
+    def determine_special_term_locations(self, k=None):
+        """Centres at ensemble quantiles, scales from neighbour spacing; tm.py:2219-2361.
+        Quantiles are order statistics of one standardised column: the column is downloaded and
+        numpy's linear-interpolation quantile is applied (setup, not hot)."""
+        cols = {}
+
+        def column(d):
+            if d not in cols:
+                cols[d] = self._column(d)
+            return cols[d]
+
+        def place(dictionary):
+            f = self.ST_scale_factor
+            for d in [key for key in dictionary.keys() if key != 'cross-terms']:
+                cnt = dictionary[d]['counter']
+                if cnt == 1:
+                    dictionary[d]['centers'] = np.asarray([np.quantile(column(d), q=0.5)])
+                    dictionary[d]['scales'] = np.asarray([f / 2 if self.ST_scale_mode == 'dynamic' else f])
+                elif cnt > 1:
+                    ctr = np.quantile(a=column(d), q=np.arange(1, cnt + 1, 1) / (cnt + 1))
+                    scales = np.zeros(cnt)
+                    if self.ST_scale_mode == 'dynamic':
+                        for i in range(cnt):
+                            if i == 0:
+                                scales[i] = (ctr[1] - ctr[0]) * f
+                            elif i == cnt - 1:
+                                scales[i] = (ctr[i] - ctr[i - 1]) * f
+                            else:
+                                scales[i] = (ctr[i + 1] - ctr[i - 1]) / 2 * f
+                    else:
+                        scales = scales + f
+                    dictionary[d]['centers'], dictionary[d]['scales'] = ctr, scales
+            return dictionary
+
+        K = np.arange(self.D) + self.skip_dimensions if k is None else [k + self.skip_dimensions]
+        for c in K:
+            c = int(c)
+            if 'cross-terms' in self.special_terms[c]:
+                self.special_terms[c]['cross-terms'] = place(copy.deepcopy(self.special_terms[c]['cross-terms']))
+            self.special_terms[c] = place(copy.deepcopy(self.special_terms[c]))
+
+    # ================================================================== plans
+    def _compile_plans(self):
+        self._host_plans = []
+        for k in range(self.D):
+            self._host_plans.append(ComponentPlan(
+                k, k + self.skip_dimensions, self._Dtot, self._family, self.polyfunc, self.polyfunc_der,
+                self.monotone[k], self.nonmonotone[k], self.special_terms, self.linearization))
+        self._free_plans()
+        self._plans = []
+        for p in self._host_plans:
+            h = B.c_void_p()
+            B.check(self._lib.ttm_plan_create(self._ctx, B.iptr(p.iblob), p.iblob.size, B.dptr(p.dblob), p.dblob.size,
+                                              B.ctypes.byref(h)))
+            self._plans.append(h)
+
+    def _refresh_special_terms(self):
+        """Special-term centres/scales moved (reset / precalculate): rebuild the double blobs."""
+        for p, h in zip(self._host_plans, self._plans):
+            if p.has_special:
+                p.build(self.special_terms)
+                B.check(self._lib.ttm_plan_update_doubles(h, B.dptr(p.dblob), p.dblob.size))
+
+    def _free_plans(self):
+        if getattr(self, '_plans', None):
+            for h in self._plans:
+                self._lib.ttm_plan_destroy(h)
+        self._plans = None
+
+    def __del__(self):
+        try:
+            self._free_plans()
+            if getattr(self, '_ctx', None):
+                self._lib.ttm_ctx_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    # ================================================================== basis matrices
+    def _basis(self, k, which, Xt, n):
+        p = self._host_plans[k]
+        m = (p.m_non, p.m_mon, p.m_dmon)[which]
+        if m == 0:
+            return None
+        Psi = self._empty(n, m)
+        B.check(self._lib.ttm_basis_eval(self._plans[k], which, B.c_void_p(Xt.data_ptr()), Xt.shape[1], n,
+                                         B.c_void_p(Psi.data_ptr()), self._stream()))
+        return Psi.cpu().numpy()
+
+    def _make_callables(self):
+        """fun_mon[k](x, self), fun_nonmon[k](x, self), der_fun_mon[k](x, self): same call signature as the
+        reference's exec'd functions (tm.py:1588-1589, 1804-1805, 2131-2132), evaluated by K-basis."""
+        def make(k, which):
+            def fun(x, _self=None):
+                x = np.asarray(x, dtype=np.float64)
+                return self._basis(k, which, self._to_colmajor(x), x.shape[0])
+            return fun
+        self.fun_nonmon = [make(k, 0) for k in range(self.D)]
+        self.fun_mon = [make(k, 1) for k in range(self.D)]
+        if self.monotonicity.lower() == 'separable monotonicity':
+            self.der_fun_mon = [make(k, 2) for k in range(self.D)]
+
+    def precalculate(self):
+        """tm.py:789-821: re-place the special terms; the Psi matrices are evaluated lazily on first
+        access (the fused kernels never read them)."""
+        self.determine_special_term_locations()
+        self._refresh_special_terms()
+        self.Psi_nonmon = _LazyList(self.D, lambda k: self._basis(k, 0, self._Xt, self._N))
+        self.Psi_mon = _LazyList(self.D, lambda k: self._basis(k, 1, self._Xt, self._N))
+        if self.monotonicity.lower() == 'separable monotonicity':
+            self.der_Psi_mon = _LazyList(self.D, lambda k: self._basis(k, 2, self._Xt, self._N))
+        self._fg_cache = {}
+
+    def reset(self, X):
+        """tm.py:710-748."""
+        if len(X.shape) != 2:
+            raise Exception('X should be a two-dimensional array of shape (N,D), N = number of samples, '
+                            'D = number of dimensions. Current shape of X is ' + str(X.shape))
+        self._load_samples(X)
+        for k in range(self.D):
+            self.coeffs_mon[k] = self.coeffs_mon[k] * 0 + self.coeffs_init
+            self.coeffs_nonmon[k] = self.coeffs_nonmon[k] * 0 + self.coeffs_init
+        self.precalculate()
+
+    def standardize(self):
+        raise NotImplementedError("standardisation happens on the device inside reset()/__init__ (K-std)")
+
+    # ================================================================== forward map
+    def _set_coeffs(self, k, coeffs_nonmon, coeffs_mon):
+        c = np.ascontiguousarray(np.concatenate((np.asarray(coeffs_nonmon, dtype=np.float64).ravel(),
+                                                 np.asarray(coeffs_mon, dtype=np.float64).ravel())))
+        p = self._host_plans[k]
+        if c.size != p.m_non + p.m_mon:
+            raise ValueError('component %d expects %d nonmonotone + %d monotone coefficients, got %d'
+                             % (k, p.m_non, p.m_mon, c.size))
+        B.check(self._lib.ttm_plan_set_coeffs(self._plans[k], B.dptr(c), self._stream()))
+
+    def _s_device(self, k, Xt, n, out):
+        """S_k on the columns of Xt into the device vector `out` (coefficients already set)."""
+        if self.monotonicity == "integrated rectifier":
+            B.check(self._lib.ttm_eval_s_ir(self._plans[k], B.c_void_p(Xt.data_ptr()), Xt.shape[1], n,
+                                            B.c_void_p(out.data_ptr()), self._stream()))
+        elif self.monotonicity == "separable monotonicity":
+            B.check(self._lib.ttm_sep_eval(self._plans[k], B.c_void_p(Xt.data_ptr()), Xt.shape[1], n,
+                                           B.c_void_p(out.data_ptr()), None, 0, None, self._stream()))
+        else:
+            raise ValueError("monotonicity must be 'integrated rectifier' or 'separable monotonicity' (case-sensitive "
+                             "in s(), tm.py:2516/2550)")
+
+    def s(self, x, k, coeffs_nonmon=None, coeffs_mon=None):
+        """k-th map component on (already standardised) samples x, or on the training ensemble if x is None
+        (tm.py:2439-2567)."""
+        if coeffs_mon is None:
+            coeffs_mon = self.coeffs_mon[k]
+        if coeffs_nonmon is None:
+            coeffs_nonmon = self.coeffs_nonmon[k]
+        if x is None:
+            Xt, n = self._Xt, self._N
+        else:
+            x = np.asarray(x, dtype=np.float64)
+            Xt, n = self._to_colmajor(x), x.shape[0]
+        self._set_coeffs(k, coeffs_nonmon, coeffs_mon)
+        out = self._empty(n)
+        self._s_device(k, Xt, n, out)
+        return out.cpu().numpy()
+
+    def map(self, X=None):
+        """Forward map target -> reference (tm.py:2391-2437)."""
+        if X is not None and self.standardize_samples:
+            X = np.asarray(X, dtype=np.float64)
+            Xt, n = self._to_colmajor(X, self._mean_d, self._std_d), X.shape[0]
+        else:
+            # NB the reference ignores a user-supplied X when standardize_samples is False (tm.py:2419-2422)
+            Xt, n = self._Xt, self._N
+        Zt = self._empty(self.D, n)
+        for k in range(self.D):
+            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+            self._s_device(k, Xt, n, Zt[k])
+        return self._to_rowmajor(Zt, n, self.D)
+
+    # ================================================================== objective + gradient (IR)
+    def _objgrad(self, coeffs, k):
+        """(J, grad) without regularisation from ONE fused launch; memoised on the coefficient bytes because
+        scipy calls `fun` and `jac` separately at the same point (tm.py:3252-3257)."""
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        key = (k, c.tobytes())
+        hit = self._fg_cache.get('key') == key
+        if not hit:
+            p = self._host_plans[k]
+            out = np.empty(1 + p.m_non + p.m_mon)
+            B.check(self._lib.ttm_objgrad_ir(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1],
+                                             self._N, B.dptr(c), B.dptr(out), self._stream()))
+            self._fg_cache = {'key': key, 'out': out}
+        return self._fg_cache['out']
+
+    def _reg_lambda(self, k, div):
+        lam = self.regularization_lambda
+        if np.isscalar(lam):
+            return lam, lam
+        if type(lam) == list:
+            return lam[k][:div], lam[k][div:]
+        raise ValueError("Data type of regularization_lambda not understood. Must be either scalar or list.")
+
+    def _split(self, coeffs, k, div):
+        if coeffs is None:
+            return np.concatenate((self.coeffs_nonmon[k], self.coeffs_mon[k])), len(self.coeffs_nonmon[k])
+        return np.asarray(coeffs, dtype=np.float64), div
+
+    def objective_function(self, coeffs, k, div=0):
+        """tm.py:3300-3433."""
+        coeffs, div = self._split(coeffs, k, div)
+        a, b = coeffs[:div], coeffs[div:]
+        objective = float(self._objgrad(coeffs, k)[0])
+        if self.regularization is not None:
+            if type(self.regularization) != str:
+                raise ValueError("The variable 'regularization' must be either None, 'l1', or 'l2'.")
+            la, lb = self._reg_lambda(k, div)
+            if self.regularization.lower() == 'l1':
+                objective += np.sum(lb * np.abs(b)) + np.sum(la * np.abs(a))
+            elif self.regularization.lower() == 'l2':
+                objective += np.sum(lb * b ** 2) + np.sum(la * a ** 2)
+            else:
+                raise ValueError("regularization_type must be either 'l1' or 'l2'.")
+        return objective
+
+    def objective_function_jacobian(self, coeffs, k, div=0):
+        """tm.py:3435-3635."""
+        if self.rectifier_type in ('squared', 'explinearunit'):
+            raise Exception("Not implemented yet.")            # rectifier.evaluate_dfdc, tm.py:5119-5163
+        coeffs, div = self._split(coeffs, k, div)
+        a, b = coeffs[:div], coeffs[div:]
+        grad = np.array(self._objgrad(coeffs, k)[1:])
+        if self.regularization is not None:
+            if type(self.regularization) != str:
+                raise ValueError("The variable 'regularization' must be either None, 'l1', or 'l2'.")
+            la, lb = self._reg_lambda(k, div)
+            if self.regularization.lower() == 'l1':
+                grad = grad + np.concatenate((la * np.sign(a), lb * np.sign(b)))
+            elif self.regularization.lower() == 'l2':
+                grad = grad + np.concatenate((la * 2 * a, lb * 2 * b))
+            else:
+                raise ValueError("regularization_type must be either 'l1' or 'l2'.")
+        return grad
+
+    # ================================================================== fitting
+    def worker_task(self, k, task_supervisor=None):
+        """BFGS on the fused objective/gradient (tm.py:3174-3298)."""
+        from scipy.optimize import minimize
+        div = len(self.coeffs_nonmon[k])
+        x0 = np.concatenate((self.coeffs_nonmon[k], self.coeffs_mon[k]))
+        opt = minimize(method='BFGS', fun=self.objective_function, jac=self.objective_function_jacobian,
+                       x0=x0, args=(k, div))
+        self._last_opt = opt
+        return (opt.x[:div].copy(), opt.x[div:].copy())
+
+    def _gram(self, k):
+        p = self._host_plans[k]
+        M = p.m_non + p.m_mon
+        G = self._empty(M, M)
+        Mp = (M + 7) // 8 * 8
+        need = Mp * Mp * min(self._sm_count, max(1, (self._N + 31) // 32))
+        if self._scratch.numel() < need:
+            self._scratch = self._empty(need)
+        B.check(self._lib.ttm_gram(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1], self._N,
+                                   B.c_void_p(G.data_ptr()), B.c_void_p(self._scratch.data_ptr()),
+                                   self._scratch.numel(), self._stream()))
+        return G.cpu().numpy()
+
+    def _separable_setup(self, k):
+        """Reduced m_mon x m_mon problem from the Gram blocks of [Psi_non | Psi_mon] (K-gram, DMMA).
+        No regularisation: A = (Gmm - Gmn Gnn^-1 Gnm)/N, which equals A_sqrt^T A_sqrt / N of the reference's QR
+        formulation (tm.py:2966-2975).  L2: the ridge normal equations of tm.py:3031-3050 (no 1/N there)."""
+        p = self._host_plans[k]
+        G = self._gram(k)
+        mn = p.m_non
+        Gnn, Gnm, Gmm = G[:mn, :mn], G[:mn, mn:], G[mn:, mn:]
+        N = self._N
+        if self.regularization is None:
+            # scaled Cholesky solve (Jacobi preconditioning tames the squared condition number)
+            d = 1.0 / np.sqrt(np.maximum(np.diag(Gnn), np.finfo(float).tiny))
+            L = np.linalg.cholesky(Gnn * d[:, None] * d[None, :])
+            Y = np.linalg.solve(L, Gnm * d[:, None])
+            A = (Gmm - Y.T @ Y) / N
+            back = lambda b: -(d * np.linalg.solve(L.T, Y @ b))
+        elif self.regularization.lower() == 'l2':
+            lam = self.regularization_lambda
+            Bm = np.linalg.solve(Gnn + lam * np.identity(mn), Gnm)
+            # (Psi_m - Psi_n B)^T (Psi_m - Psi_n B) expanded in Gram blocks
+            R = Gmm - Gnm.T @ Bm - Bm.T @ Gnm + Bm.T @ Gnn @ Bm
+            A = R / 2 + lam * (Bm.T @ Bm + np.identity(Bm.shape[-1]))
+            back = lambda b: -np.linalg.solve(Gnn + 2 * lam * np.identity(mn), Gnm @ b)
+        else:
+            raise ValueError("separable monotonicity supports regularization None or 'l2'")
+        return 0.5 * (A + A.T), back
+
+    def _sep_objective(self, b, A, k):
+        """(f, grad) of the reduced problem, tm.py:2978-3006; the N-long sums come from K-sepobj."""
+        p = self._host_plans[k]
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        out = np.empty(1 + p.m_dmon)
+        B.check(self._lib.ttm_sep_objgrad(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1],
+                                          self._N, B.dptr(b), B.dptr(out), self._stream()))
+        N = self._N
+        bvec = self.delta * np.sum(A, axis=-1)
+        Ax = A @ b
+        f = b @ Ax / 2 - out[0] / N + b @ bvec
+        g = Ax - out[1:] / N + bvec
+        return f, g
+
+    def worker_task_monotone(self, k, task_supervisor=None):
+        """Separable fit of component k (tm.py:2903-3172)."""
+        from scipy.optimize import minimize
+        if self._host_plans[k].m_non == 0:
+            raise ValueError("separable monotonicity requires at least one nonmonotone term per component "
+                             "(the reference's np.linalg.qr(None) fails too)")
+        A, back = self._separable_setup(k)
+        bounds = [[self.optimization_constraints_lb[k][i], self.optimization_constraints_ub[k][i]]
+                  for i in range(len(self.optimization_constraints_lb[k]))]
+        opt = minimize(fun=lambda b, A, k: self._sep_objective(b, A, k), method='L-BFGS-B',
+                       x0=copy.copy(self.coeffs_mon[k]), jac=True, bounds=bounds, args=(A, k))
+        self._last_opt = opt
+        return (back(opt.x), opt.x)
+
+    def optimize(self, K=None):
+        """tm.py:2714-2901.  Components are independent; with torch.distributed initialised they are sharded
+        over the ranks (longest first, like the reference's Pool over np.flip(K)) and the coefficients are
+        gathered with one all-gather."""
+        if K is None:
+            K = np.arange(self.D)
+        K = [int(k) for k in K]
+        fit = self.worker_task if self.monotonicity == "integrated rectifier" else self.worker_task_monotone
+        from .parallel import shard_components, allgather_coeffs, world
+        rank, size = world()
+        mine = shard_components(K, rank, size)
+        results = {}
+        for k in mine:
+            results[k] = fit(k, None)
+            if self.verbose and size == 1:
+                print('\r' + 'Progress: |' + (K.index(k) + 1) * '█' + (len(K) - K.index(k) - 1) * ' ' + '|', end='\r')
+        if size > 1:
+            results = allgather_coeffs(results, K, [self._host_plans[k].m_non for k in K],
+                                       [self._host_plans[k].m_mon for k in K], self._device)
+        for k in K:
+            self.coeffs_nonmon[k] = copy.deepcopy(results[k][0])
+            self.coeffs_mon[k] = copy.deepcopy(results[k][1])
+
+    # ================================================================== inverse map
+    def inverse_map(self, Z, X_star=None):
+        """Inverse map reference -> target, optionally conditioned on X_star (tm.py:3639-3796)."""
+        Z = np.asarray(Z, dtype=np.float64)
+        N = Z.shape[0]
+        skip, D = self.skip_dimensions, self.D
+        if X_star is None:
+            ncol, comps, E = skip + D, [(k, k) for k in range(D)], 0
+        else:
+            X_star = np.asarray(X_star, dtype=np.float64)
+            if X_star.shape[-1] == skip:
+                ncol, comps, E = skip + D, [(k, k) for k in range(D)], skip
+            elif skip == 0:
+                E = X_star.shape[-1]
+                ncol, comps = E + Z.shape[-1], [(i, k) for i, k in enumerate(range(E, E + Z.shape[-1]))]
+            else:
+                raise UnboundLocalError("X_star has %d columns; expected skip_dimensions = %d" % (X_star.shape[-1], skip))
+        if ncol != self._Dtot:
+            raise ValueError("operands could not be broadcast together: %d columns vs %d" % (ncol, self._Dtot))
+        torch = self._torch
+        Xw = torch.zeros(ncol, N, dtype=torch.float64, device=self._device)
+        if E > 0:
+            std = self.standardize_samples
+            Xs = self._to_colmajor(X_star, self._mean_d[:E].contiguous() if std else None,
+                                   self._std_d[:E].contiguous() if std else None)
+            Xw[:E] = Xs
+        Zt = self._to_colmajor(Z)
+        table_mode = self.alternate_root_finding and self.monotonicity.lower() == 'separable monotonicity'
+        for i, k in comps:
+            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+            if table_mode:
+                self._root_search_table(k, Xw, N, Zt[i])
+            else:
+                self._root_search_bisection(k, Xw, N, Zt[i])
+        if self.standardize_samples:
+            Xout = self._to_rowmajor(Xw[skip:], N, ncol - skip, self._mean_d[skip:].contiguous(),
+                                     self._std_d[skip:].contiguous())
+        else:
+            Xout = self._to_rowmajor(Xw[skip:], N, ncol - skip)
+        return Xout
+
+    def _root_search_table(self, k, Xw, N, z, start_distance=10, resolution=1001):
+        """vectorized_root_search_alternate (tm.py:3987-4084): table on the device, argsort on the host
+        (scipy interp1d sorts its abscissae), interpolation per sample on the device."""
+        pts = np.linspace(-start_distance, start_distance, resolution)
+        tab = self._empty(2 * resolution)
+        tab[resolution:] = self._upload(pts)
+        B.check(self._lib.ttm_mon_table(self._plans[k], resolution, B.c_void_p(tab.data_ptr()), self._stream()))
+        out = tab[:resolution].cpu().numpy()
+        ind = np.argsort(out, kind="mergesort")
+        tab = self._upload(np.concatenate((out[ind], pts[ind])))
+        B.check(self._lib.ttm_inverse_table(self._plans[k], B.c_void_p(Xw.data_ptr()), Xw.shape[1], N,
+                                            B.c_void_p(z.data_ptr()), B.c_void_p(tab.data_ptr()), resolution,
+                                            1 if self.root_search_truncation else 0, self._stream()))
+
+    def _root_search_bisection(self, k, Xw, N, z, max_iterations=100):
+        """vectorized_root_search_bisection (tm.py:3798-3985), one thread per sample."""
+        stalled = B.c_int(0)
+        sep = 1 if self.monotonicity.lower() == 'separable monotonicity' else 0
+        B.check(self._lib.ttm_inverse_bisect(self._plans[k], B.c_void_p(Xw.data_ptr()), Xw.shape[1], N,
+                                             B.c_void_p(z.data_ptr()), sep, max_iterations,
+                                             B.ctypes.byref(stalled), self._stream()))
+        if stalled.value and self.verbose:
+            print('WARNING: root search for %d particles stopped at maximum iterations.' % stalled.value)
+
+    # ================================================================== densities (separable only)
+    def _log_det_accumulate(self, acc, Xraw_t, n, Zt, mode, std_offset):
+        dS = self._empty(n)
+        for k in range(self.D):
+            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+            # NB the reference evaluates the derivative basis on the UNstandardised samples (tm.py:2627, 2695)
+            B.check(self._lib.ttm_sep_eval(self._plans[k], None, 0, n, None, B.c_void_p(Xraw_t.data_ptr()),
+                                           Xraw_t.shape[1], B.c_void_p(dS.data_ptr()), self._stream()))
+            sigma = float(self.X_std[k + std_offset]) if self.standardize_samples else None
+            if sigma is None:
+                sigma = float(self.X_std[k + std_offset])        # AttributeError like the reference
+            B.check(self._lib.ttm_density_accumulate(self._ctx, B.c_void_p(acc.data_ptr()),
+                                                     B.c_void_p(Zt[k].data_ptr()) if Zt is not None else None,
+                                                     B.c_void_p(dS.data_ptr()), sigma, mode, n, self._stream()))
+
+    def evaluate_pullback_density(self, X, X_star=None):
+        """tm.py:2646-2712."""
+        assert self.monotonicity == "separable monotonicity", "evaluate_pushforward_density is currently only implemented for monotonicity = 'separable monotonicity'."
+        X = np.asarray(X, dtype=np.float64)
+        if X_star is not None:
+            X = np.column_stack((X_star, X))
+        n = X.shape[0]
+        torch = self._torch
+        if self.standardize_samples:
+            Xt = self._to_colmajor(X, self._mean_d, self._std_d)
+        else:
+            Xt, n = self._Xt, self._N
+        Xraw_t = self._to_colmajor(X)
+        Zt = self._empty(self.D, n)
+        for k in range(self.D):
+            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+            self._s_device(k, Xt, n, Zt[k])
+        acc = torch.zeros(n, dtype=torch.float64, device=self._device)
+        self._log_det_accumulate(acc, Xraw_t, n, Zt, 0, 0)      # X_std[k] (not k+skip), tm.py:2706
+        out = self._empty(n)
+        B.check(self._lib.ttm_density_finish(self._ctx, B.c_void_p(acc.data_ptr()), None,
+                                             B.c_void_p(out.data_ptr()), n, self._stream()))
+        return out.cpu().numpy()
+
+    def evaluate_pushforward_density(self, Z, log_target_pdf, X_star=None):
+        """tm.py:2569-2644.  `log_target_pdf` is a user Python callback on host arrays."""
+        assert self.monotonicity == "separable monotonicity", "evaluate_pushforward_density is currently only implemented for monotonicity = 'separable monotonicity'."
+        X = self.inverse_map(Z, X_star)
+        log_target = np.ascontiguousarray(log_target_pdf(X), dtype=np.float64)
+        if X_star is not None:
+            X = np.column_stack((X_star, X))
+        n = X.shape[0]
+        torch = self._torch
+        Xraw_t = self._to_colmajor(X)
+        acc = torch.zeros(n, dtype=torch.float64, device=self._device)
+        self._log_det_accumulate(acc, Xraw_t, n, None, 1, self.skip_dimensions)   # X_std[k+skip], tm.py:2638
+        out = self._empty(n)
+        lt = self._upload(log_target)
+        B.check(self._lib.ttm_density_finish(self._ctx, B.c_void_p(acc.data_ptr()), B.c_void_p(lt.data_ptr()),
+                                             B.c_void_p(out.data_ptr()), n, self._stream()))
+        return out.cpu().numpy()
+
+    # ================================================================== measurement helpers
+    def fp64_peak_tflops(self):
+        v = B.c_double(0.0)
+        B.check(self._lib.ttm_fp64_peak(self._ctx, B.ctypes.byref(v)))
+        return v.value
