@@ -1,0 +1,339 @@
+"""
+bench.py -- headline metric of BASELINE.json on B200:
+
+    objective+gradient evals/sec at N = 1M, K = 64   (config C4 of SURVEY.md section 8(d):
+    synthetic D = 64 map, order-3 Hermite-function integrated rectifier, Q = 100 quadrature nodes)
+
+One *eval* = one (J_k, grad J_k) pair of ONE component over all N samples, i.e. what one
+`objective_function` + `objective_function_jacobian` callback pair of scipy costs in the reference
+(tm.py:3300 + :3435).  One *step* = the 64 evals of all components (one pass of the hot path over
+the ensemble).  With --gpus N the 64 components are sharded over the ranks (strong scaling, no
+data-path collective); value = 64 * steps / max-over-ranks device time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the CPU port of the reference algorithm (oracle/ttm_oracle.py, component-
+parallel over all host cores like the reference's multiprocessing Pool, tm.py:2789-2845) on a bounded
+sample of the same workload.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+from cases import synthetic_samples, c4_terms    # noqa: E402  (workload recipe shared with the parity tests)
+
+D, N_FULL, Q = 64, 1_000_000, 100
+METRIC = 'objective+gradient evals/sec at N=1M, K=64'
+UNIT = 'evals/s'
+
+
+def flops_per_eval(k, n, q=Q, m_mon=4):
+    """Algorithmic FP64 work of one eval (frozen instruction costs c_exp=30, c_log=47):
+    node loop Q*(8 + c_exp + m_m + 2 m_m + c_exp + 2 + 1 + 2 m_m) + x_<c part 48 k + epilogue 75, per sample."""
+    mm = 3 if k == 0 else m_mon
+    node = q * (8 + 30 + mm + 2 * mm + 30 + 2 + 1 + 2 * mm)
+    return n * (node + 48 * k + 75)
+
+
+def bytes_per_eval(k, n):
+    return 8 * n * (k + 1)
+
+
+def coefficients(mon, non, seed=0):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal(len(non[k]) + len(mon[k])) * 0.05 for k in range(len(mon))]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.samples, self.active = gpu_index, [], False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                p = [t.strip() for t in line.split(',')]
+                if len(p) >= 8 and p[0] == str(self.gpu_index) and self.active:
+                    self.samples.append(p)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm = sorted(float(s[1]) for s in self.samples)
+        reasons = []
+        for idx, name in ((4, 'hw_slowdown'), (5, 'hw_thermal_slowdown'), (6, 'sw_thermal_slowdown'), (7, 'sw_power_cap')):
+            if any(s[idx].lower().startswith('active') for s in self.samples):
+                reasons.append(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][2]),
+                'power_w_max': max(float(s[3]) for s in self.samples), 'reasons': reasons, 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, component-parallel like the reference's Pool
+# ------------------------------------------------------------------------------------------------
+_OM = None
+
+
+def _cpu_eval(args):
+    k, c = args
+    div = len(_OM.coeffs_nonmon[k])
+    t = time.perf_counter()
+    f = _OM.objective_function(c, k, div)
+    g = _OM.objective_function_jacobian(c, k, div)
+    return time.perf_counter() - t, float(f), float(np.linalg.norm(g))
+
+
+def cpu_port(n_sample, ks, workers, steps=1, warmup=0):
+    """Times objective+jacobian of the listed components on an n_sample-row sample of the C4 workload.
+    Returns (evals/s scaled linearly to N = 1M, seconds per step)."""
+    global _OM
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from ttm_oracle import OracleMap
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1' if workers > 1 else str(os.cpu_count()))
+    X = synthetic_samples(n_sample, D, seed=0)
+    mon, non = c4_terms(D)
+    _OM = OracleMap(X=X, monotone=mon, nonmonotone=non, monotonicity='integrated rectifier',
+                    quadrature_input={'order': Q})
+    coefs = coefficients(mon, non)
+    work = [(k, coefs[k]) for k in sorted(ks, reverse=True)]      # longest first (tm.py:2821)
+    times = []
+    if workers > 1:
+        from multiprocessing import get_context
+        with get_context('fork').Pool(workers) as pool:
+            for s in range(warmup + steps):
+                t = time.perf_counter()
+                pool.map(_cpu_eval, work, chunksize=1)
+                if s >= warmup:
+                    times.append(time.perf_counter() - t)
+    else:
+        for s in range(warmup + steps):
+            t = time.perf_counter()
+            for w in work:
+                _cpu_eval(w)
+            if s >= warmup:
+                times.append(time.perf_counter() - t)
+    per_step = float(np.mean(times))
+    return len(ks) / per_step * (n_sample / N_FULL), per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, D))
+    n_sample = 4000
+    t0 = time.perf_counter()
+    value, per_step = cpu_port(n_sample, list(range(D)), workers, steps=args.steps, warmup=min(args.warmup, 1))
+    sample = ('all 64 components of C4 (D=64, Q=100) on the first %d samples, evals/s scaled linearly to N=1M '
+              '(the port materialises every Psi like the reference: N=1M needs ~54 GB)' % n_sample)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': min(args.warmup, 1), 'ms_per_step': per_step * 1e3 * (N_FULL / n_sample), 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'C4: synthetic D=64 integrated-rectifier map, order-3 Hermite functions, Q=100, N=1M',
+                   'sample_rows': n_sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'wall_s': time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from transport_map import transport_map
+    from ttt_b200 import binding as B
+    from ttt_b200.parallel import shard_components
+
+    n = args.n
+    X = synthetic_samples(n, D, seed=0)
+    mon, non = c4_terms(D)
+    tm = transport_map(X=X, monotone=mon, nonmonotone=non, polynomial_type='hermite function',
+                       monotonicity='integrated rectifier', quadrature_input={'order': Q}, verbose=False)
+    del X
+    coefs = coefficients(mon, non)
+    mine = shard_components(list(range(D)), rank, world)
+    lib, stream = tm._lib, tm._stream()
+    Xp, ld = B.c_void_p(tm._Xt.data_ptr()), tm._Xt.shape[1]
+    for k in mine:
+        tm._set_coeffs(k, coefs[k][:len(non[k])], coefs[k][len(non[k]):])
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')   # 512 MB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(events=None):
+        for k in mine:
+            if events is not None:
+                events[k][0].record()
+            B.check(lib.ttm_objgrad_ir_launch(tm._plans[k], Xp, ld, n, stream))
+            if events is not None:
+                events[k][1].record()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- value: inputs resident in HBM, device time only
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler.active = True
+    t_steps, per_k = [], {k: [] for k in mine}
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(float(s))                       # L2 flush between timed iterations (outside the event pair)
+        ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in mine}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident(ev)
+        e1.record()
+        torch.cuda.synchronize()
+        t_steps.append(e0.elapsed_time(e1) * 1e-3)
+        for k in mine:
+            per_k[k].append(ev[k][0].elapsed_time(ev[k][1]) * 1e-3)
+    barrier()
+    wall_value = time.perf_counter() - wall0
+    t_local = float(sum(t_steps))
+
+    # ---- e2e: through the public class API with host coefficient vectors in, host (J, grad) out
+    rng = np.random.default_rng(1)
+
+    def step_e2e(s):
+        tot = 0.0
+        for k in mine:
+            c = coefs[k] + 1e-6 * (s + 1)           # new point every step: no memoised result is reused
+            div = len(non[k])
+            tot += tm.objective_function(c, k, div)
+            g = tm.objective_function_jacobian(c, k, div)
+            tot += g[0]
+        return tot
+
+    for s in range(args.warmup):
+        step_e2e(-s - 1)
+    barrier()
+    w0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(s)
+    torch.cuda.synchronize()
+    t_e2e_local = time.perf_counter() - w0
+    barrier()
+    sampler.active = False
+    sampler.stop()
+
+    tt = torch.tensor([t_local, t_e2e_local], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max, t_e2e = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        value = D * args.steps / t_max
+        e2e_value = D * args.steps / t_e2e
+        # dominant kernel = the fused objgrad kernel (every launch of the timed region is one)
+        kt = {k: float(np.mean(v)) for k, v in per_k.items()}
+        fl = sum(flops_per_eval(k, n) for k in mine)
+        by = sum(bytes_per_eval(k, n) for k in mine)
+        t_kernels = sum(kt.values())
+        fp64_peak = tm.fp64_peak_tflops()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        achieved = fl / t_kernels / 1e12
+        roofline = {
+            'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
+            'traffic': None,
+            'peak_source': 'ttm_fp64_peak: dependent-free DFMA chains, measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
+            'flops_per_launch_avg': fl / len(mine), 'bytes_per_launch_avg': by / len(mine),
+            'launch_ms_avg': t_kernels / len(mine) * 1e3,
+            'hbm': {'achieved_gbs': by / t_kernels / 1e9, 'peak_gbs': hbm_peak, 'frac': by / t_kernels / 1e9 / hbm_peak,
+                    'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback'},
+            'per_k': {str(k): {'ms': kt[k] * 1e3, 'tflops': flops_per_eval(k, n) / kt[k] / 1e12,
+                               'evals_per_s': 1.0 / kt[k]} for k in (0, 31, 63) if k in kt},
+        }
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': t_max / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'C4: synthetic D=64 integrated-rectifier map, order-3 Hermite functions, Q=%d, N=%d' % (Q, n),
+                       'components': D, 'samples': n, 'quadrature_order': Q, 'parallelism': 'components sharded over %d GPU(s)' % world,
+                       'l2': 'flushed between timed steps (512 MB write); the sample matrix itself is %d MB' % (8 * n * D >> 20)},
+            'e2e': {'value': e2e_value, 'unit': UNIT,
+                    'h2d_bytes_per_step': int(sum(8 * len(coefs[k]) for k in range(D))),
+                    'd2h_bytes_per_step': int(sum(8 * (1 + len(coefs[k])) for k in range(D))),
+                    'api': 'transport_map.objective_function + objective_function_jacobian per component (host numpy in/out)'},
+            'gpu_launches': D * args.steps,
+            'roofline': roofline,
+            'clocks': sampler.summary(),
+            'wall_s_value_region': wall_value,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            ks = [0, 31, 63]
+            n_cpu = 20000
+            v, per = cpu_port(n_cpu, ks, 1)
+            line['cpu_baseline'] = {
+                'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                'sample': 'components k=0,31,63 of the same C4 map on %d samples (single process, BLAS threads = %s), '
+                          'evals/s scaled linearly to N=1M; host has %d cores' % (n_cpu, os.environ.get('OPENBLAS_NUM_THREADS'), cores)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--n', type=int, default=N_FULL, help='samples (default: the metric point, 1M)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -90,6 +90,23 @@ class PlanInterp:
         out = np.full((X.shape[0], m), np.nan)
         for j in self.ib[h[PL.H_CONST_IDX]:h[PL.H_CONST_IDX] + h[PL.H_NCONST]]:
             out[:, j] = 1.0
+        nd, dmax = int(h[PL.H_NDENSE]), int(h[PL.H_DENSE_MAXORD])
+        stride = 2 * (dmax + 1)
+        dvar = self.ib[h[PL.H_DENSE_VAR]:h[PL.H_DENSE_VAR] + 4 * nd].reshape(nd, 4)
+        didx = self.ib[h[PL.H_DENSE_IDX]:h[PL.H_DENSE_IDX] + nd * stride].reshape(nd, stride)
+        dsc = self.db[h[PL.H_D_DENSE_SCALE]:h[PL.H_D_DENSE_SCALE] + nd * stride].reshape(nd, stride)
+        P = _FAMS[self.family]
+        for g in range(nd):
+            col, gmax, has_hf, has_plain = (int(t) for t in dvar[g])
+            x = X[:, col]
+            assert gmax <= dmax and np.all(didx[g, 2 * (gmax + 1):] < 0) and np.all(didx[g, :2] < 0)
+            for s in range(stride):
+                j = int(didx[g, s])
+                if j < 0:
+                    continue
+                o, hf = divmod(s, 2)
+                assert (has_hf if hf else has_plain)
+                out[:, j] = dsc[g, s] * P([0.] * o + [1.])(x) * (np.exp(-x ** 2 / 4) if hf else 1.0)
         nv = int(h[PL.H_NVARS])
         var = self.ib[h[PL.H_VAR_IDX]:h[PL.H_VAR_IDX] + 2 * nv].reshape(nv, 2)
         ptr = self.ib[h[PL.H_VAR_PTR]:h[PL.H_VAR_PTR] + nv + 1]
@@ -97,15 +114,8 @@ class PlanInterp:
         ei = self.ib[h[PL.H_ENT_I]:h[PL.H_ENT_I] + 4 * ne].reshape(ne, 4)
         ed = self.db[h[PL.H_D_ENT]:h[PL.H_D_ENT] + 4 * ne].reshape(ne, 4)
         for g in range(nv):
-            last_order, seen_st = 0, False
             for e in range(ptr[g], ptr[g + 1]):
                 kind, order, j, _ = (int(t) for t in ei[e])
-                if kind <= PL.F_POLY_HF:
-                    assert not seen_st and order >= last_order, 'entries must be sorted: polynomials by order, then special terms'
-                    assert kind == PL.F_POLY or (var[g, 1] & 1), 'HF flag missing on the variable group'
-                    last_order = order
-                else:
-                    seen_st = True
                 out[:, j] = factor(kind, order, ed[e, 0], 0.0, ed[e, 1], ed[e, 2], self.family, X[:, var[g, 0]])
         full = self.terms(0, X)
         for j in self.ib[h[PL.H_MULTI_IDX]:h[PL.H_MULTI_IDX] + h[PL.H_NMULTI]]:

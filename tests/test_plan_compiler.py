@@ -39,7 +39,7 @@ def test_compiled_tables_reproduce_oracle_basis(name):
         h = plan.iblob
         from ttt_b200 import plan as PL
         assert h[PL.H_FAC_I] % 4 == 0 and h[PL.H_ENT_I] % 4 == 0 and h[PL.H_VAR_IDX] % 2 == 0
-        assert h[PL.H_D_FAC] % 4 == 0 and h[PL.H_D_ENT] % 4 == 0
+        assert h[PL.H_D_FAC] % 4 == 0 and h[PL.H_D_ENT] % 4 == 0 and h[PL.H_DENSE_VAR] % 4 == 0
 
 
 def test_bad_options_raise_like_the_reference():

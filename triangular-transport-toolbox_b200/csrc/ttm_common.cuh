@@ -52,6 +52,8 @@ enum {
     // double blob offsets (in doubles)
     H_D_FAC, H_D_ENT, H_D_SLOT_SCALE, H_D_REC,
     H_NON_MAXVAR,   // 1 + largest column index touched by the nonmonotone terms
+    // dense nonmonotone groups: per variable, polynomial coefficients addressed by slot 2*order+hf
+    H_NDENSE, H_DENSE_VAR, H_DENSE_IDX, H_DENSE_MAXORD, H_D_DENSE_SCALE,
     H_SIZE = 48
 };
 
@@ -61,12 +63,14 @@ struct PlanView {
     int dtot, c, family, nfac;
     int m_non, m_mon, m_dmon;
     int nconst, nvars, nmulti;
+    int ndense, dense_maxord;
     int maxord, has_plain, has_hf, nst, nslot;
     // offsets
     int o_fac_i, o_non_ptr, o_non_fac, o_mon_ptr, o_mon_fac, o_dmon_ptr, o_dmon_fac;
     int o_const_idx, o_var_idx, o_var_ptr, o_ent_i, o_multi_idx;
     int o_slot_ptr, o_slot_term, o_out_ptr, o_out_fac, o_st_fac;
     int o_d_fac, o_d_ent, o_d_slot_scale, o_d_rec;
+    int o_dense_var, o_dense_idx, o_d_dense_scale;
 };
 
 // ---------------------------------------------------------------------------------------

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(T_INV) inverse_table_kernel(const InvArgs a) {
             idx[r] = ok[r] ? i : a.N - 1;
             S[r] = 0.0;
         }
-        nonmon_sweep<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);   // offset (:4039-4043)
+        nonmon_sweep_rt<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);   // offset (:4039-4043)
 #pragma unroll
         for (int r = 0; r < R_OBJ; ++r) {
             if (!ok[r]) continue;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(T_INV) inverse_bisect_kernel(const InvArgs a) 
             idx[r] = ok[r] ? i : a.first;
             S[r] = 0.0;
         }
-        nonmon_sweep<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);
+        nonmon_sweep_rt<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);
 #pragma unroll 1
         for (int r = 0; r < R_OBJ; ++r) {
             if (!ok[r]) continue;

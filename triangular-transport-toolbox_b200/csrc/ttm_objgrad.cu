@@ -1,5 +1,7 @@
 // Dispatcher of K-objgrad / K-S: picks the narrowest compiled instantiation that covers the
 // component's slot structure (see ttm_objgrad_impl.cuh for the kernel).
+#include <cstdlib>
+
 #include "ttm_objgrad_impl.cuh"
 
 // Returns cudaErrorInvalidValue if the plan exceeds the compiled limits (order > 20 or > 8
@@ -13,7 +15,9 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaSt
     const int64_t rows = (a.N + T_OBJ - 1) / T_OBJ;
     const int nslot_rt = 2 * (P.maxord + 1) + P.nst;
     auto smem_for = [&](int maxord_t) {
-        return sizeof(double) * (size_t)(m + 2 * a.Q + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0));
+        return sizeof(double) * (size_t)(m + 2 * (a.Q + 4) + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0) +
+                                        (size_t)P.ndense * 2 * (P.dense_maxord + 1) * 2 + 2 * P.ndense + 2) +
+               sizeof(int) * (size_t)(P.ndense * 2 * (P.dense_maxord + 1) + 4);
     };
     auto grid_for = [&](int blocks_per_sm) {
         int64_t g = (int64_t)sm_count * blocks_per_sm;
@@ -21,8 +25,18 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaSt
         if (g > a.max_grid) g = a.max_grid;
         return (int)(g < 1 ? 1 : g);
     };
-    if (P.nst == 0 && herme && exprect && !P.has_plain && P.maxord <= 3)
-        return ttm_objgrad_cfg0(a, grad, grid_for(4), smem_for(3), st);
+    if (P.nst == 0 && herme && exprect && !P.has_plain && P.maxord <= 3) {
+        // tuning variants of the hot instantiation (RB samples x NQ nodes in flight per thread)
+        static const int variant = getenv("TTM_OBJ_VARIANT") ? atoi(getenv("TTM_OBJ_VARIANT")) : 0;
+        static const int bps = getenv("TTM_OBJ_BPS") ? atoi(getenv("TTM_OBJ_BPS")) : 4;
+        switch (variant) {
+            case 6: return ttm_objgrad_cfg6(a, grad, grid_for(bps), smem_for(3), st);
+            case 7: return ttm_objgrad_cfg7(a, grad, grid_for(bps), smem_for(3), st);
+            case 8: return ttm_objgrad_cfg8(a, grad, grid_for(bps), smem_for(3), st);
+            case 9: return ttm_objgrad_cfg9(a, grad, grid_for(bps), smem_for(3), st);
+            default: return ttm_objgrad_cfg0(a, grad, grid_for(bps), smem_for(3), st);
+        }
+    }
     if (P.nst == 0 && herme && exprect && P.maxord <= 3)
         return ttm_objgrad_cfg1(a, grad, grid_for(4), smem_for(3), st);
     if (P.nst == 0 && herme && exprect && P.maxord <= 6)

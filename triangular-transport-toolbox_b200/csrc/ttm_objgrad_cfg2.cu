@@ -2,5 +2,5 @@
 #include "ttm_objgrad_impl.cuh"
 
 cudaError_t ttm_objgrad_cfg2(const ObjArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) {
-    return ttm_obj::launch_cfg<6, true, true, 0, true, true, 2>(a, grad, grid, smem, st);
+    return ttm_obj::launch_cfg<6, true, true, 0, true, true, 2, 1>(a, grad, grid, smem, st);
 }

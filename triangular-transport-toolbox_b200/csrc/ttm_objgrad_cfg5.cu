@@ -2,5 +2,5 @@
 #include "ttm_objgrad_impl.cuh"
 
 cudaError_t ttm_objgrad_cfg5(const ObjArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) {
-    return ttm_obj::launch_cfg<20, true, true, 8, false, false, 1>(a, grad, grid, smem, st);
+    return ttm_obj::launch_cfg<20, true, true, 8, false, false, 1, 1>(a, grad, grid, smem, st);
 }

@@ -55,7 +55,7 @@ static __device__ __noinline__ double outer_product(const PlanView& P, int j, co
     return v;
 }
 
-template <int MAXORD, bool HAS_PLAIN, bool HAS_HF, int NST, bool HERME, bool EXPRECT, bool GRAD, int RB>
+template <int MAXORD, bool HAS_PLAIN, bool HAS_HF, int NST, bool HERME, bool EXPRECT, bool GRAD, int RB, int NQ>
 __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     extern __shared__ double smem[];
     const PlanView& P = a.P;
@@ -68,16 +68,24 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     const int nslot_rt = st_base + P.nst;
 
     double* s_coef = smem;
+    const int Qp = (a.Q + NQ - 1) / NQ * NQ;            // node count padded to a multiple of NQ
     double* s_xis = s_coef + m;
-    double* s_ws = s_xis + a.Q;
-    double* s_rec = s_ws + a.Q;
+    double* s_ws = s_xis + Qp;
+    double* s_rec = s_ws + Qp;
     double* s_scale = s_rec + 3 * (MAXORD + 1);
     double* s_gacc = s_scale + nslot_rt;
+    // dense nonmonotone tables staged after the gradient slots: coefficient products, scales, indices, groups
+    const int dstride = 2 * (P.dense_maxord + 1);
+    const int ndt = P.ndense * dstride;
+    double* s_dprod = s_gacc + (GRAD ? NW * (1 + m) : 0);
+    double* s_dscale = s_dprod + ndt;
+    int4* s_dvar = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(s_dscale + ndt) + 15) & ~uintptr_t(15));
+    int* s_didx = reinterpret_cast<int*>(s_dvar + P.ndense);
 
     for (int j = tid; j < m; j += T_OBJ) s_coef[j] = a.coeffs[j];
-    for (int q = tid; q < a.Q; q += T_OBJ) {
-        s_xis[q] = a.xis[q];
-        s_ws[q] = a.ws[q];
+    for (int q = tid; q < Qp; q += T_OBJ) {              // padding nodes: mid-point, zero weight
+        s_xis[q] = (q < a.Q) ? a.xis[q] : 0.0;
+        s_ws[q] = (q < a.Q) ? a.ws[q] : 0.0;
     }
     for (int n = tid; n < 3 * (MAXORD + 1); n += T_OBJ) {
         double A, B, C;
@@ -87,7 +95,17 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     for (int s = tid; s < nslot_rt; s += T_OBJ) s_scale[s] = P.db[P.o_d_slot_scale + s];
     if (GRAD)
         for (int j = tid; j < NW * (1 + m); j += T_OBJ) s_gacc[j] = 0.0;
+    for (int e = tid; e < ndt; e += T_OBJ) {
+        const int j = P.ib[P.o_dense_idx + e];
+        const double sc = P.db[P.o_d_dense_scale + e];
+        s_didx[e] = j;
+        s_dscale[e] = sc;
+        s_dprod[e] = (j >= 0) ? a.coeffs[j] * sc : 0.0;
+    }
+    for (int g = tid; g < P.ndense; g += T_OBJ) s_dvar[g] = reinterpret_cast<const int4*>(P.ib + P.o_dense_var)[g];
     __syncthreads();
+    DenseTabs DT;
+    DT.var = s_dvar; DT.idx = s_didx; DT.scale = s_dscale; DT.coefprod = s_dprod;
 
     const double* acoef = s_coef;
     const double* bcoef = s_coef + P.m_non;
@@ -128,11 +146,17 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
             S[r] = 0.0;
         }
         // ---------------- phase A ----------------
-        nonmon_sweep<false>(P, Xt, ld, idx, acoef, S, gslot, lane);
+        nonmon_sweep<false, HERME>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
 
         // ---------------- phase B ----------------
 #pragma unroll 1
         for (int r0 = 0; r0 < R_OBJ; r0 += RB) {
+            if (row0 + r0 >= row_hi) {       // rows past the block's range (uniform over the block)
+#pragma unroll
+                for (int r = 0; r < R_OBJ; ++r)
+                    if (r >= r0) S[r] = 0.0;
+                break;
+            }
             double hx[RB], xc[RB], Sacc[RB];
             double Cp[MAXORD + 1][RB], Ch[MAXORD + 1][RB], Cs[NSTA][RB];
             double Ip[MAXORD + 1][RB], Ih[MAXORD + 1][RB], Is[NSTA][RB];
@@ -182,7 +206,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 ladder<MAXORD, HERME>(t, s_rec, Pl);
                 double r = 0.0;
                 if (HAS_HF) {
-                    ga = exp(-0.25 * t * t);
+                    ga = ttm_exp_neg(-0.25 * t * t);
                     double u = 0.0;
 #pragma unroll
                     for (int o = 1; o <= MAXORD; ++o) u = fma(Ch[o][rb], Pl[o], u);
@@ -204,29 +228,32 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
 
             // ---- Gauss-Legendre node loop (transport_map.py:4252-4278) ----
 #pragma unroll 1
-            for (int q = 0; q < a.Q; ++q) {
-                const double xi = s_xis[q], w = s_ws[q];
+            for (int q = 0; q < Qp; q += NQ) {
 #pragma unroll
-                for (int rb = 0; rb < RB; ++rb) {
-                    const double t = fma(hx[rb], xi, hx[rb]);
-                    double Pl[MAXORD + 1], ga = 1.0, sv[NSTA];
-                    const double r = inner(rb, t, Pl, ga, sv);
-                    const double g = EXPRECT ? exp(r) : rect_eval(a.rect, r);
-                    Sacc[rb] = fma(w, g, Sacc[rb]);
-                    if (GRAD) {
-                        const double wd = w * (EXPRECT ? g : rect_dfac(a.rect, r, g));
-                        if (HAS_PLAIN) {
+                for (int u = 0; u < NQ; ++u) {
+                    const double xi = s_xis[q + u], w = s_ws[q + u];
 #pragma unroll
-                            for (int o = 0; o <= MAXORD; ++o) Ip[o][rb] = fma(wd, Pl[o], Ip[o][rb]);
-                        }
-                        if (HAS_HF) {
-                            const double wg = wd * ga;
+                    for (int rb = 0; rb < RB; ++rb) {
+                        const double t = fma(hx[rb], xi, hx[rb]);
+                        double Pl[MAXORD + 1], ga = 1.0, sv[NSTA];
+                        const double r = inner(rb, t, Pl, ga, sv);
+                        const double g = EXPRECT ? ttm_exp(r) : rect_eval(a.rect, r);
+                        Sacc[rb] = fma(w, g, Sacc[rb]);
+                        if (GRAD) {
+                            const double wd = w * (EXPRECT ? g : rect_dfac(a.rect, r, g));
+                            if (HAS_PLAIN) {
 #pragma unroll
-                            for (int o = 1; o <= MAXORD; ++o) Ih[o][rb] = fma(wg, Pl[o], Ih[o][rb]);
-                        }
-                        if (NST > 0) {
+                                for (int o = 0; o <= MAXORD; ++o) Ip[o][rb] = fma(wd, Pl[o], Ip[o][rb]);
+                            }
+                            if (HAS_HF) {
+                                const double wg = wd * ga;
 #pragma unroll
-                            for (int qq = 0; qq < NST; ++qq) Is[qq][rb] = fma(wd, sv[qq], Is[qq][rb]);
+                                for (int o = 1; o <= MAXORD; ++o) Ih[o][rb] = fma(wg, Pl[o], Ih[o][rb]);
+                            }
+                            if (NST > 0) {
+#pragma unroll
+                                for (int qq = 0; qq < NST; ++qq) Is[qq][rb] = fma(wd, sv[qq], Is[qq][rb]);
+                            }
                         }
                     }
                 }
@@ -242,7 +269,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 if (GRAD) {
                     double Plx[MAXORD + 1], gax = 1.0, svx[NSTA];
                     const double rc = inner(rb, xc[rb], Plx, gax, svx);
-                    const double gc = EXPRECT ? exp(rc) : rect_eval(a.rect, rc);
+                    const double gc = EXPRECT ? ttm_exp(rc) : rect_eval(a.rect, rc);
                     const double L = rect_log(a.rect, rc, gc, a.delta);
                     ratio[rb] = (EXPRECT ? gc : rect_dfac(a.rect, rc, gc)) / (gc + a.delta);
                     Jacc += valid[r0 + rb] * (0.5 * Sfull[rb] * Sfull[rb] - L);
@@ -295,7 +322,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 if (valid[r] != 0.0) a.S_out[idx[r]] = S[r];
         } else {
             // ---------------- phase C ----------------
-            nonmon_sweep<true>(P, Xt, ld, idx, acoef, S, gslot, lane);
+            nonmon_sweep<true, HERME>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
         }
     }
 
@@ -329,15 +356,15 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     }
 }
 
-template <int MAXORD, bool HAS_PLAIN, bool HAS_HF, int NST, bool HERME, bool EXPRECT, int RB>
+template <int MAXORD, bool HAS_PLAIN, bool HAS_HF, int NST, bool HERME, bool EXPRECT, int RB, int NQ>
 cudaError_t launch_cfg(const ObjArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) {
     cudaError_t e;
     if (grad) {
-        auto k = objgrad_kernel<MAXORD, HAS_PLAIN, HAS_HF, NST, HERME, EXPRECT, true, RB>;
+        auto k = objgrad_kernel<MAXORD, HAS_PLAIN, HAS_HF, NST, HERME, EXPRECT, true, RB, NQ>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<grid, T_OBJ, smem, st>>>(a);
     } else {
-        auto k = objgrad_kernel<MAXORD, HAS_PLAIN, HAS_HF, NST, HERME, EXPRECT, false, RB>;
+        auto k = objgrad_kernel<MAXORD, HAS_PLAIN, HAS_HF, NST, HERME, EXPRECT, false, RB, NQ>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<grid, T_OBJ, smem, st>>>(a);
     }
@@ -348,14 +375,18 @@ cudaError_t launch_cfg(const ObjArgs& a, bool grad, int grid, size_t smem, cudaS
 
 // one exported launcher per instantiation (defined in ttm_objgrad_cfg<N>.cu)
 #define TTM_OBJ_CFG_LIST(X)                          \
-    X(0, 3, false, true, 0, true, true, 2)           \
-    X(1, 3, true, true, 0, true, true, 2)            \
-    X(2, 6, true, true, 0, true, true, 2)            \
-    X(3, 12, true, true, 0, true, true, 1)           \
-    X(4, 6, true, true, 0, false, false, 2)          \
-    X(5, 20, true, true, 8, false, false, 1)
+    X(0, 3, false, true, 0, true, true, 2, 1)        \
+    X(1, 3, true, true, 0, true, true, 2, 1)         \
+    X(2, 6, true, true, 0, true, true, 2, 1)         \
+    X(3, 12, true, true, 0, true, true, 1, 1)        \
+    X(4, 6, true, true, 0, false, false, 2, 1)       \
+    X(5, 20, true, true, 8, false, false, 1, 1)      \
+    X(6, 3, false, true, 0, true, true, 2, 2)        \
+    X(7, 3, false, true, 0, true, true, 4, 1)        \
+    X(8, 3, false, true, 0, true, true, 1, 2)        \
+    X(9, 3, false, true, 0, true, true, 1, 4)
 
-#define TTM_OBJ_DECL(ID, MAXORD, HP, HH, NST, HERME, EXPR, RB) \
+#define TTM_OBJ_DECL(ID, MAXORD, HP, HH, NST, HERME, EXPR, RB, NQ) \
     cudaError_t ttm_objgrad_cfg##ID(const ObjArgs& a, bool grad, int grid, size_t smem, cudaStream_t st);
 TTM_OBJ_CFG_LIST(TTM_OBJ_DECL)
 #undef TTM_OBJ_DECL

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const
             S[r] = 0.0;
         }
         if (S_out) {
-            nonmon_sweep<false>(P, Xt, ld, idx, acoef, S, nullptr, 0);
+            nonmon_sweep_rt<false>(P, Xt, ld, idx, acoef, S, nullptr, 0);
             for (int j = 0; j < P.m_mon; ++j) {
                 const double b = bcoef[j];
 #pragma unroll

@@ -29,7 +29,8 @@ PLAN_MAGIC = 0x54544d31
  H_M_NON, H_NON_PTR, H_NON_FAC, H_M_MON, H_MON_PTR, H_MON_FAC, H_M_DMON, H_DMON_PTR, H_DMON_FAC,
  H_NCONST, H_CONST_IDX, H_NVARS, H_VAR_IDX, H_VAR_PTR, H_ENT_I, H_NMULTI, H_MULTI_IDX,
  H_MAXORD, H_HAS_PLAIN, H_HAS_HF, H_NST, H_NSLOT, H_SLOT_PTR, H_SLOT_TERM, H_OUT_PTR, H_OUT_FAC, H_ST_FAC,
- H_D_FAC, H_D_ENT, H_D_SLOT_SCALE, H_D_REC, H_NON_MAXVAR) = range(38)
+ H_D_FAC, H_D_ENT, H_D_SLOT_SCALE, H_D_REC, H_NON_MAXVAR,
+ H_NDENSE, H_DENSE_VAR, H_DENSE_IDX, H_DENSE_MAXORD, H_D_DENSE_SCALE) = range(43)
 H_SIZE = 48
 
 _ST_KIND = {'rbf': F_RBF, 'irbf': F_IRBF, 'let': F_LET, 'ret': F_RET}
@@ -224,9 +225,27 @@ class ComponentPlan:
                 groups.setdefault(int(fi[t[0], 0]), []).append((t[0], j))
             else:
                 multi_idx.append(j)
-        var_idx, var_ptr, ent_i, ent_d = [], [0], [], []
+        # dense groups: polynomial terms of one variable addressed by slot 2*order+hf (first occurrence of a
+        # slot; duplicates and special terms go to the generic "slow" groups)
+        dense_maxord = max([int(fi[f, 2]) for v in groups for f, _ in groups[v] if fi[f, 1] <= F_POLY_HF], default=0)
+        stride = 2 * (dense_maxord + 1)
+        dense_var, dense_idx, dense_scale, slow = [], [], [], {}
         for v in sorted(groups):
-            ents = sorted(groups[v], key=lambda e: (0, fi[e[0], 2]) if fi[e[0], 1] <= F_POLY_HF else (1, 0))
+            idx_row, sc_row = -np.ones(stride, dtype=np.int32), np.zeros(stride)
+            for f, j in groups[v]:
+                slot = 2 * int(fi[f, 2]) + int(fi[f, 1] == F_POLY_HF)
+                if fi[f, 1] <= F_POLY_HF and idx_row[slot] < 0:
+                    idx_row[slot], sc_row[slot] = j, fd[f, 0]
+                else:
+                    slow.setdefault(v, []).append((f, j))
+            used = np.nonzero(idx_row >= 0)[0]
+            if len(used):
+                dense_var.append((v, int(used.max() // 2), int(np.any(used % 2 == 1)), int(np.any(used % 2 == 0))))
+                dense_idx.append(idx_row)
+                dense_scale.append(sc_row)
+        var_idx, var_ptr, ent_i, ent_d = [], [0], [], []
+        for v in sorted(slow):
+            ents = sorted(slow[v], key=lambda e: (0, fi[e[0], 2]) if fi[e[0], 1] <= F_POLY_HF else (1, 0))
             flags = 1 if any(fi[f, 1] == F_POLY_HF for f, _ in ents) else 0
             var_idx.append((v, flags))
             for f, j in ents:
@@ -324,6 +343,10 @@ class ComponentPlan:
         h[H_D_SLOT_SCALE] = put_d(slot_scale)
         h[H_D_REC] = put_d(np.zeros(1))
         h[H_NON_MAXVAR] = non_maxvar
+        h[H_NDENSE], h[H_DENSE_MAXORD] = len(dense_var), dense_maxord
+        h[H_DENSE_VAR] = put_i(dense_var, 4)
+        h[H_DENSE_IDX] = put_i(np.concatenate(dense_idx) if dense_idx else [])
+        h[H_D_DENSE_SCALE] = put_d(np.concatenate(dense_scale) if dense_scale else [])
         self.iblob = np.ascontiguousarray(np.concatenate(ib), dtype=np.int32)
         self.dblob = np.ascontiguousarray(np.concatenate(db), dtype=np.float64)
         self.maxord, self.nst, self.nslot = maxord, nst, nslot
