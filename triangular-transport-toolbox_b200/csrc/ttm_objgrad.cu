@@ -17,7 +17,8 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaSt
     auto smem_for = [&](int maxord_t) {
         return sizeof(double) * (size_t)(m + 2 * (a.Q + 4) + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0) +
                                         (size_t)P.ndense * 2 * (P.dense_maxord + 1) * 2 + 2 * P.ndense + 2) +
-               sizeof(int) * (size_t)(P.ndense * 2 * (P.dense_maxord + 1) + 4);
+               sizeof(int) * (size_t)(P.ndense * 2 * (P.dense_maxord + 1) + 8) +
+               (grad ? sizeof(double) * (size_t)(ttm_obj::CH_ROWS * T_OBJ + 2) : 0);
     };
     auto grid_for = [&](int blocks_per_sm) {
         int64_t g = (int64_t)sm_count * blocks_per_sm;
@@ -27,14 +28,14 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaSt
     };
     if (P.nst == 0 && herme && exprect && !P.has_plain && P.maxord <= 3) {
         // tuning variants of the hot instantiation (RB samples x NQ nodes in flight per thread)
-        static const int variant = getenv("TTM_OBJ_VARIANT") ? atoi(getenv("TTM_OBJ_VARIANT")) : 0;
+        static const int variant = getenv("TTM_OBJ_VARIANT") ? atoi(getenv("TTM_OBJ_VARIANT")) : 6;
         static const int bps = getenv("TTM_OBJ_BPS") ? atoi(getenv("TTM_OBJ_BPS")) : 4;
         switch (variant) {
-            case 6: return ttm_objgrad_cfg6(a, grad, grid_for(bps), smem_for(3), st);
+            case 0: return ttm_objgrad_cfg0(a, grad, grid_for(bps), smem_for(3), st);
             case 7: return ttm_objgrad_cfg7(a, grad, grid_for(bps), smem_for(3), st);
             case 8: return ttm_objgrad_cfg8(a, grad, grid_for(bps), smem_for(3), st);
             case 9: return ttm_objgrad_cfg9(a, grad, grid_for(bps), smem_for(3), st);
-            default: return ttm_objgrad_cfg0(a, grad, grid_for(bps), smem_for(3), st);
+            default: return ttm_objgrad_cfg6(a, grad, grid_for(bps), smem_for(3), st);  // RB=2 samples x NQ=2 nodes
         }
     }
     if (P.nst == 0 && herme && exprect && P.maxord <= 3)

@@ -28,7 +28,8 @@
 
 namespace ttm_obj {
 
-constexpr int T_OBJ = 128;  // threads per block
+constexpr int T_OBJ = 128;   // threads per block
+constexpr int CH_ROWS = 16;  // rows per chunk between two dense phase-C passes (multiple of R_OBJ)
 
 // ---- polynomial ladder on the inner variable: fills P[0..MAXORD] ----
 template <int MAXORD, bool HERME>
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     double* s_dscale = s_dprod + ndt;
     int4* s_dvar = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(s_dscale + ndt) + 15) & ~uintptr_t(15));
     int* s_didx = reinterpret_cast<int*>(s_dvar + P.ndense);
+    double* s_S = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_didx + ndt) + 15) & ~uintptr_t(15));  // [CH_ROWS][T_OBJ]
 
     for (int j = tid; j < m; j += T_OBJ) s_coef[j] = a.coeffs[j];
     for (int q = tid; q < Qp; q += T_OBJ) {              // padding nodes: mid-point, zero weight
@@ -134,13 +136,15 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     const int64_t rows = (N + T_OBJ - 1) / T_OBJ;
     const int64_t row_lo = rows * blockIdx.x / gridDim.x, row_hi = rows * (blockIdx.x + 1) / gridDim.x;
 
-    for (int64_t row0 = row_lo; row0 < row_hi; row0 += R_OBJ) {
+    for (int64_t chunk_lo = row_lo; chunk_lo < row_hi; chunk_lo += CH_ROWS) {
+    const int64_t chunk_hi = (chunk_lo + CH_ROWS < row_hi) ? chunk_lo + CH_ROWS : row_hi;
+    for (int64_t row0 = chunk_lo; row0 < chunk_hi; row0 += R_OBJ) {
         int64_t idx[R_OBJ];
         double valid[R_OBJ], S[R_OBJ];
 #pragma unroll
         for (int r = 0; r < R_OBJ; ++r) {
             const int64_t i = (row0 + r) * T_OBJ + tid;
-            const bool ok = (row0 + r < row_hi) && (i < N);
+            const bool ok = (row0 + r < chunk_hi) && (i < N);
             valid[r] = ok ? 1.0 : 0.0;
             idx[r] = ok ? i : (N - 1);
             S[r] = 0.0;
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
         // ---------------- phase B ----------------
 #pragma unroll 1
         for (int r0 = 0; r0 < R_OBJ; r0 += RB) {
-            if (row0 + r0 >= row_hi) {       // rows past the block's range (uniform over the block)
+            if (row0 + r0 >= chunk_hi) {     // rows past the chunk (uniform over the block)
 #pragma unroll
                 for (int r = 0; r < R_OBJ; ++r)
                     if (r >= r0) S[r] = 0.0;
@@ -322,8 +326,15 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 if (valid[r] != 0.0) a.S_out[idx[r]] = S[r];
         } else {
             // ---------------- phase C ----------------
-            nonmon_sweep<true, HERME>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
+            // constants / special terms / multivariate terms per row group; dense groups per chunk below
+            nonmon_sweep<true, HERME, false>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
+#pragma unroll
+            for (int r = 0; r < R_OBJ; ++r)
+                if (row0 + r < chunk_hi) s_S[(row0 + r - chunk_lo) * T_OBJ + tid] = S[r];
         }
+    }
+    if (GRAD)
+        nonmon_grad_dense_chunk<HERME, 4>(P, DT, Xt, ld, chunk_lo, chunk_hi, N, T_OBJ, tid, s_S, gslot, lane);
     }
 
     if (!GRAD) return;
