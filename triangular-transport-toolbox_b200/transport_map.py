@@ -90,14 +90,21 @@ class transport_map():
                  adaptation_max_order=10,
                  adaptation_skip_dimensions=0,
                  adaptation_max_iterations=25,
-                 device=None):
+                 device=None,
+                 sample_sharded=False):
         """Same arguments as the reference constructor (tm.py:12-168).  `device` (extra, optional)
-        selects the CUDA device index; default: torch's current device."""
+        selects the CUDA device index; default: torch's current device.  `sample_sharded` (extra, optional):
+        with torch.distributed initialised, X is this rank's shard of the ensemble; statistics, objective,
+        gradient and Gram matrices are all-reduced so that every rank fits every component in lockstep
+        (the K < #GPUs case of SURVEY.md 8(e)); default: components are sharded instead."""
         torch = _torch()
         self._torch = torch
         self._dev_index = torch.cuda.current_device() if device is None else int(device)
         self._device = torch.device('cuda', self._dev_index)
         self._lib = B.lib()
+        from .parallel import world
+        self._rank, self._world = world()
+        self._sharded = bool(sample_sharded) and self._world > 1
 
         self.monotone = copy.deepcopy(monotone)
         self.nonmonotone = copy.deepcopy(nonmonotone)
@@ -222,7 +229,13 @@ class transport_map():
                             'D = number of dimensions. Current shape of X is ' + str(X.shape))
         n, d = X.shape
         self._N, self._Dtot = n, d
+        self._N_global = n
         self._X_host = None
+        if self._sharded and (not self.standardize_samples or self.standardization.lower() != 'standard'):
+            from .parallel import allreduce_sum
+            self._N_global = int(round(allreduce_sum(np.array([float(n)]), self._device)[0]))
+            if self.standardize_samples:
+                raise NotImplementedError("sample_sharded supports standardization='standard' only")
         if not self.standardize_samples:
             self._Xt = self._to_colmajor(X)
             self._mean_d = self._std_d = None
@@ -235,6 +248,15 @@ class transport_map():
                                            B.c_void_p(self._mean_d.data_ptr()), B.c_void_p(self._std_d.data_ptr()),
                                            B.c_void_p(self._scratch.data_ptr()), self._stream()))
             self._Xt = self._empty(d, n)
+            if self._sharded:
+                # exact combination of the per-shard moments: one all-reduce of [n, n*mean, n*(var + mean^2)]
+                from .parallel import allreduce_sum
+                mu, sd = self._mean_d.cpu().numpy(), self._std_d.cpu().numpy()
+                tot = allreduce_sum(np.concatenate(([float(n)], n * mu, n * (sd ** 2 + mu ** 2))), self._device)
+                self._N_global = int(round(tot[0]))
+                gmu = tot[1:1 + d] / tot[0]
+                gsd = np.sqrt(np.maximum(tot[1 + d:] / tot[0] - gmu ** 2, 0.0))
+                self._mean_d, self._std_d = self._upload(gmu), self._upload(gsd)
             B.check(self._lib.ttm_standardize_transpose(self._ctx, B.c_void_p(Xd.data_ptr()), n, d,
                                                         B.c_void_p(self._mean_d.data_ptr()),
                                                         B.c_void_p(self._std_d.data_ptr()),
@@ -268,7 +290,13 @@ class transport_map():
         self._X_host = None
 
     def _column(self, d):
-        return self._Xt[d].cpu().numpy()
+        col = self._Xt[d].cpu().numpy()
+        if self._sharded:                      # order statistics need the whole column (setup, once per reset)
+            import torch.distributed as dist
+            parts = [None] * self._world
+            dist.all_gather_object(parts, col)
+            col = np.concatenate(parts)
+        return col
 
     # ================================================================== special terms
     def check_for_special_terms(self):
@@ -481,6 +509,9 @@ class transport_map():
             out = np.empty(1 + p.m_non + p.m_mon)
             B.check(self._lib.ttm_objgrad_ir(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1],
                                              self._N, B.dptr(c), B.dptr(out), self._stream()))
+            if self._sharded:                  # sample means -> global mean: one all-reduce of (1+m) doubles
+                from .parallel import allreduce_sum
+                out = allreduce_sum(out * self._N, self._device) / self._N_global
             self._fg_cache = {'key': key, 'out': out}
         return self._fg_cache['out']
 
@@ -555,7 +586,11 @@ class transport_map():
         B.check(self._lib.ttm_gram(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1], self._N,
                                    B.c_void_p(G.data_ptr()), B.c_void_p(self._scratch.data_ptr()),
                                    self._scratch.numel(), self._stream()))
-        return G.cpu().numpy()
+        G = G.cpu().numpy()
+        if self._sharded:
+            from .parallel import allreduce_sum
+            G = allreduce_sum(G.ravel(), self._device).reshape(G.shape)
+        return G
 
     def _separable_setup(self, k):
         """Reduced m_mon x m_mon problem from the Gram blocks of [Psi_non | Psi_mon] (K-gram, DMMA).
@@ -565,7 +600,7 @@ class transport_map():
         G = self._gram(k)
         mn = p.m_non
         Gnn, Gnm, Gmm = G[:mn, :mn], G[:mn, mn:], G[mn:, mn:]
-        N = self._N
+        N = self._N_global
         if self.regularization is None:
             # scaled Cholesky solve (Jacobi preconditioning tames the squared condition number)
             d = 1.0 / np.sqrt(np.maximum(np.diag(Gnn), np.finfo(float).tiny))
@@ -591,7 +626,10 @@ class transport_map():
         out = np.empty(1 + p.m_dmon)
         B.check(self._lib.ttm_sep_objgrad(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1],
                                           self._N, B.dptr(b), B.dptr(out), self._stream()))
-        N = self._N
+        if self._sharded:
+            from .parallel import allreduce_sum
+            out = allreduce_sum(out, self._device)
+        N = self._N_global
         bvec = self.delta * np.sum(A, axis=-1)
         Ax = A @ b
         f = b @ Ax / 2 - out[0] / N + b @ bvec
@@ -622,6 +660,8 @@ class transport_map():
         fit = self.worker_task if self.monotonicity == "integrated rectifier" else self.worker_task_monotone
         from .parallel import shard_components, allgather_coeffs, world
         rank, size = world()
+        if self._sharded:
+            rank, size = 0, 1                  # every rank fits every component on its shard, in lockstep
         mine = shard_components(K, rank, size)
         results = {}
         for k in mine:
