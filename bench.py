@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-from cases import synthetic_samples, c4_terms    # noqa: E402  (workload recipe shared with the parity tests)
+from cases import synthetic_samples, c4_terms, c5_terms    # noqa: E402  (workload recipes shared with the parity tests)
 
 D, N_FULL, Q = 64, 1_000_000, 100
 METRIC = 'objective+gradient evals/sec at N=1M, K=64'
@@ -166,6 +166,52 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary metric M2: conditional sampling via inverse_map (config C5)
+# ------------------------------------------------------------------------------------------------
+def inverse_metric(rank, world, dist, torch):
+    """C5: D=256 separable map (LET/iRBF/iRBF/RET + order-3 nonmonotone terms), trained on 10^4
+    samples (components sharded over the ranks, one all-gather), then inverse_map(Z, X_star) with E=128
+    conditioning columns on 1.25M samples PER GPU (10M over 8 GPUs), through the public class API with host
+    arrays in and out.  Samples shard with no collective."""
+    from transport_map import transport_map
+    Dm, E, ntrain, ns = 256, 128, 10000, 1_250_000
+    mon, non = c5_terms(Dm)
+    t = time.perf_counter()
+    tm = transport_map(X=synthetic_samples(ntrain, Dm, seed=0), monotone=mon, nonmonotone=non,
+                       monotonicity='separable monotonicity', verbose=False)
+    ctor_s = time.perf_counter() - t
+    t = time.perf_counter()
+    tm.optimize()
+    torch.cuda.synchronize()
+    opt_s = time.perf_counter() - t
+    rng = np.random.default_rng(100 + rank)
+    Xstar = synthetic_samples(ns, Dm, seed=200 + rank)[:, :E].copy()
+    Z = rng.standard_normal((ns, Dm - E))
+    res = {}
+    for mode, alt, n_use in (('table', True, ns), ('bisection', False, 250_000)):
+        tm.alternate_root_finding = alt
+        tm.inverse_map(Z[:2000], X_star=Xstar[:2000])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = time.perf_counter()
+        Xs = tm.inverse_map(Z[:n_use], X_star=Xstar[:n_use])
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        res[mode] = {'samples_per_s': n_use * world / float(dt[0]), 'samples': n_use * world, 'seconds': float(dt[0])}
+        if not alt:
+            resid = float(np.max(np.abs(tm.map(Xs[:20000])[:, E:] - Z[:20000])))
+            res[mode]['max_residual'] = resid
+    return {'metric': 'inverse_map samples/sec', 'value': res['table']['samples_per_s'], 'unit': 'samples/s',
+            'config': {'workload': 'C5: D=256 separable map, conditional sampling with E=128, %d samples per GPU, '
+                                   'default table root finder (alternate_root_finding=True)' % ns, 'n_train': ntrain},
+            'bisection': res['bisection'], 'table': res['table'], 'ctor_s': ctor_s, 'optimize_s': opt_s,
+            'scaling': 'weak', 'e2e': True}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
@@ -258,10 +304,17 @@ def run_gpu(args):
     sampler.active = False
     sampler.stop()
 
+    fp64_peak_tflops = tm.fp64_peak_tflops() if rank == 0 else 0.0
     tt = torch.tensor([t_local, t_e2e_local], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_max, t_e2e = float(tt[0]), float(tt[1])
+
+    inv = None
+    if not args.no_inverse:
+        del tm, flush
+        torch.cuda.empty_cache()
+        inv = inverse_metric(rank, world, dist, torch)
 
     if rank == 0:
         value = D * args.steps / t_max
@@ -271,7 +324,7 @@ def run_gpu(args):
         fl = sum(flops_per_eval(k, n) for k in mine)
         by = sum(bytes_per_eval(k, n) for k in mine)
         t_kernels = sum(kt.values())
-        fp64_peak = tm.fp64_peak_tflops()
+        fp64_peak = fp64_peak_tflops
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -315,6 +368,8 @@ def run_gpu(args):
                 'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                 'sample': 'components k=0,31,63 of the same C4 map on %d samples (single process, BLAS threads = %s), '
                           'evals/s scaled linearly to N=1M; host has %d cores' % (n_cpu, os.environ.get('OPENBLAS_NUM_THREADS'), cores)}
+        if inv is not None:
+            line['inverse_map'] = inv
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -328,6 +383,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--n', type=int, default=N_FULL, help='samples (default: the metric point, 1M)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-inverse', action='store_true', help='skip the secondary inverse_map metric (config C5)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

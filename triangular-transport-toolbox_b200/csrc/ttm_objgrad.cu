@@ -16,9 +16,9 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaSt
     const int nslot_rt = 2 * (P.maxord + 1) + P.nst;
     auto smem_for = [&](int maxord_t) {
         return sizeof(double) * (size_t)(m + 2 * (a.Q + 4) + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0) +
-                                        (size_t)P.ndense * 2 * (P.dense_maxord + 1) * 2 + 2 * P.ndense + 2) +
+                                        (size_t)P.ndense * 2 * (P.dense_maxord + 1) * 2 + 2 * P.ndense + 6) +
                sizeof(int) * (size_t)(P.ndense * 2 * (P.dense_maxord + 1) + 8) +
-               (grad ? sizeof(double) * (size_t)(ttm_obj::CH_ROWS * T_OBJ + 2) : 0);
+               sizeof(double) * (size_t)(ttm_obj::CH_ROWS * T_OBJ + 2);
     };
     auto grid_for = [&](int blocks_per_sm) {
         int64_t g = (int64_t)sm_count * blocks_per_sm;

@@ -29,7 +29,8 @@
 namespace ttm_obj {
 
 constexpr int T_OBJ = 128;   // threads per block
-constexpr int CH_ROWS = 16;  // rows per chunk between two dense phase-C passes (multiple of R_OBJ)
+constexpr int CH_ROWS = 16;  // rows per chunk between two dense phase-C passes (multiple of R_OBJ and RC_SWEEP)
+constexpr int RC_SWEEP = 4;  // rows per thread in flight in the dense sweeps (8 independent exp chains)
 
 // ---- polynomial ladder on the inner variable: fills P[0..MAXORD] ----
 template <int MAXORD, bool HERME>
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     // dense nonmonotone tables staged after the gradient slots: coefficient products, scales, indices, groups
     const int dstride = 2 * (P.dense_maxord + 1);
     const int ndt = P.ndense * dstride;
-    double* s_dprod = s_gacc + (GRAD ? NW * (1 + m) : 0);
+    double* s_dprod = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_gacc + (GRAD ? NW * (1 + m) : 0)) + 15) & ~uintptr_t(15));
     double* s_dscale = s_dprod + ndt;
     int4* s_dvar = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(s_dscale + ndt) + 15) & ~uintptr_t(15));
     int* s_didx = reinterpret_cast<int*>(s_dvar + P.ndense);
@@ -108,6 +109,9 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     __syncthreads();
     DenseTabs DT;
     DT.var = s_dvar; DT.idx = s_didx; DT.scale = s_dscale; DT.coefprod = s_dprod;
+    DenseSmem DS;
+    DS.o_var = (int)(reinterpret_cast<double*>(s_dvar) - smem); DS.o_idx = (int)(reinterpret_cast<double*>(s_didx) - smem);
+    DS.o_scale = (int)(s_dscale - smem); DS.o_prod = (int)(s_dprod - smem);
 
     const double* acoef = s_coef;
     const double* bcoef = s_coef + P.m_non;
@@ -138,6 +142,20 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
 
     for (int64_t chunk_lo = row_lo; chunk_lo < row_hi; chunk_lo += CH_ROWS) {
     const int64_t chunk_hi = (chunk_lo + CH_ROWS < row_hi) ? chunk_lo + CH_ROWS : row_hi;
+    // ---------------- phase A, dense groups: S_non of the whole chunk -> s_S ----------------
+    for (int64_t row8 = chunk_lo; row8 < chunk_hi; row8 += RC_SWEEP) {
+        bool okr[RC_SWEEP];
+        double S8[RC_SWEEP];
+#pragma unroll
+        for (int r = 0; r < RC_SWEEP; ++r) {
+            okr[r] = (row8 + r < chunk_hi) && ((row8 + r) * T_OBJ + tid < N);
+            S8[r] = 0.0;
+        }
+        dense_value_smem<HERME, 3, RC_SWEEP>(P, DS, Xt, ld, row8 * T_OBJ + tid, T_OBJ, okr, S8);
+#pragma unroll
+        for (int r = 0; r < RC_SWEEP; ++r)
+            if (row8 + r < chunk_hi) s_S[(row8 + r - chunk_lo) * T_OBJ + tid] = S8[r];
+    }
     for (int64_t row0 = chunk_lo; row0 < chunk_hi; row0 += R_OBJ) {
         int64_t idx[R_OBJ];
         double valid[R_OBJ], S[R_OBJ];
@@ -147,10 +165,10 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
             const bool ok = (row0 + r < chunk_hi) && (i < N);
             valid[r] = ok ? 1.0 : 0.0;
             idx[r] = ok ? i : (N - 1);
-            S[r] = 0.0;
+            S[r] = (row0 + r < chunk_hi) ? s_S[(row0 + r - chunk_lo) * T_OBJ + tid] : 0.0;
         }
         // ---------------- phase A ----------------
-        nonmon_sweep<false, HERME>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
+        nonmon_sweep<false, HERME, false>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
 
         // ---------------- phase B ----------------
 #pragma unroll 1
@@ -231,6 +249,67 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
             };
 
             // ---- Gauss-Legendre node loop (transport_map.py:4252-4278) ----
+            if (NST == 0) {
+                // staged ("vector") form: L = NQ x RB node-samples advance through every stage together
+                constexpr int L = NQ * RB;
+#pragma unroll 1
+                for (int q = 0; q < Qp; q += NQ) {
+                    double t[L], Pl[L][MAXORD + 1], ga[L], r[L], g[L];
+#pragma unroll
+                    for (int l = 0; l < L; ++l) t[l] = fma(hx[l % RB], s_xis[q + l / RB], hx[l % RB]);
+#pragma unroll
+                    for (int l = 0; l < L; ++l) ladder<MAXORD, HERME>(t[l], s_rec, Pl[l]);
+                    if (HAS_HF) {
+                        double y[L];
+#pragma unroll
+                        for (int l = 0; l < L; ++l) y[l] = -0.25 * t[l] * t[l];
+                        ttm_exp_neg_v<L>(y, ga);
+#pragma unroll
+                        for (int l = 0; l < L; ++l) r[l] = Ch[1][l % RB] * Pl[l][1];
+#pragma unroll
+                        for (int o = 2; o <= MAXORD; ++o) {
+#pragma unroll
+                            for (int l = 0; l < L; ++l) r[l] = fma(Ch[o][l % RB], Pl[l][o], r[l]);
+                        }
+#pragma unroll
+                        for (int l = 0; l < L; ++l) r[l] *= ga[l];
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < L; ++l) { r[l] = 0.0; ga[l] = 1.0; }
+                    }
+                    if (HAS_PLAIN) {
+#pragma unroll
+                        for (int o = 0; o <= MAXORD; ++o) {
+#pragma unroll
+                            for (int l = 0; l < L; ++l) r[l] = fma(Cp[o][l % RB], Pl[l][o], r[l]);
+                        }
+                    }
+                    if (EXPRECT) {
+                        ttm_exp_v<L>(r, g);
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < L; ++l) g[l] = rect_eval(a.rect, r[l]);
+                    }
+#pragma unroll
+                    for (int l = 0; l < L; ++l) {
+                        const int rb = l % RB;
+                        const double w = s_ws[q + l / RB];
+                        Sacc[rb] = fma(w, g[l], Sacc[rb]);
+                        if (GRAD) {
+                            const double wd = w * (EXPRECT ? g[l] : rect_dfac(a.rect, r[l], g[l]));
+                            if (HAS_PLAIN) {
+#pragma unroll
+                                for (int o = 0; o <= MAXORD; ++o) Ip[o][rb] = fma(wd, Pl[l][o], Ip[o][rb]);
+                            }
+                            if (HAS_HF) {
+                                const double wg = wd * ga[l];
+#pragma unroll
+                                for (int o = 1; o <= MAXORD; ++o) Ih[o][rb] = fma(wg, Pl[l][o], Ih[o][rb]);
+                            }
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int q = 0; q < Qp; q += NQ) {
 #pragma unroll
@@ -261,6 +340,8 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                         }
                     }
                 }
+            }
+
             }
 
             // ---- per-sample epilogue ----
@@ -334,7 +415,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
         }
     }
     if (GRAD)
-        nonmon_grad_dense_chunk<HERME, 4>(P, DT, Xt, ld, chunk_lo, chunk_hi, N, T_OBJ, tid, s_S, gslot, lane);
+        dense_grad_chunk_smem<HERME, 3, RC_SWEEP>(P, DS, Xt, ld, chunk_lo, chunk_hi, N, T_OBJ, tid, s_S, gslot, lane);
     }
 
     if (!GRAD) return;
