@@ -1,0 +1,132 @@
+"""Edge cases of the CUDA path against the oracle: ragged sample counts (not a multiple of the 128-thread
+rows, fewer samples than one row, a single sample), a component without nonmonotone terms, a constant-only
+nonmonotone part, higher polynomial orders (generic instantiations, order-chunked sweeps), empty conditioning,
+duplicated terms, and reset() with a different ensemble size."""
+
+import numpy as np
+import pytest
+
+from cases import synthetic_samples, c4_terms, ex05_terms
+from harness import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_cuda(X, **kw):
+    from transport_map import transport_map
+    return transport_map(X=X, verbose=False, **kw)
+
+
+def make_oracle(X, **kw):
+    from ttm_oracle import OracleMap
+    return OracleMap(X=X, **kw)
+
+
+def compare_objgrad(tm, om, seed=0, tol=1e-10, scale=0.2):
+    rng = np.random.default_rng(seed)
+    for k in range(tm.D):
+        div = len(tm.coeffs_nonmon[k])
+        c = rng.standard_normal(div + len(tm.coeffs_mon[k])) * scale
+        assert abs(tm.objective_function(c, k, div) - om.objective_function(c, k, div)) <= tol * max(1, abs(om.objective_function(c, k, div)))
+        assert rel_err(tm.objective_function_jacobian(c, k, div), om.objective_function_jacobian(c, k, div)) <= tol
+        tm.coeffs_nonmon[k], tm.coeffs_mon[k] = c[:div].copy(), c[div:].copy()
+        om.coeffs_nonmon[k], om.coeffs_mon[k] = c[:div].copy(), c[div:].copy()
+
+
+@pytest.mark.parametrize('n', [1, 2, 31, 127, 128, 129, 513, 1000, 4097])
+def test_ragged_sample_counts(n):
+    X = synthetic_samples(max(n, 2), 3, seed=n)[:n] if n > 1 else np.array([[0.3, -0.2, 0.9]])
+    mon, non = c4_terms(3)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='integrated rectifier', standardize_samples=(n > 1))
+    tm = make_cuda(X.copy(), quadrature_input={'order': 12}, **kw)
+    om = make_oracle(X.copy(), quadrature_input={'order': 12}, **kw)
+    compare_objgrad(tm, om, seed=n)
+    assert rel_err(tm.map(X.copy()), om.map(X.copy())) <= 1e-9
+    Z = np.random.default_rng(n).standard_normal((n, 3))
+    assert np.max(np.abs(tm.inverse_map(Z.copy()) - om.inverse_map(Z.copy()))) <= 2e-8
+
+
+def test_component_without_nonmonotone_terms_and_constant_only():
+    X = synthetic_samples(300, 3, seed=2)
+    mon = [[[0], [0, 0, 'HF']], [[1], [0, 1, 'HF']], [[2, 'HF'], [2, 2, 'HF'], [0, 1, 2, 'HF']]]
+    non = [[], [[]], [[], [0, 1], [0, 'HF']]]
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='integrated rectifier')
+    tm = make_cuda(X.copy(), quadrature_input={'order': 16}, **kw)
+    om = make_oracle(X.copy(), quadrature_input={'order': 16}, **kw)
+    assert tm.Psi_nonmon[0] is None and om.Psi_nonmon[0] is None
+    compare_objgrad(tm, om)
+    assert rel_err(tm.map(X.copy()), om.map(X.copy())) <= 1e-9
+
+
+@pytest.mark.parametrize('family', ['hermite function', 'legendre', 'power series'])
+def test_high_orders_use_generic_instantiations(family):
+    """Monotone order up to 14 (generic <20, 8> instantiation), nonmonotone order 9 (order-chunked sweeps),
+    duplicated nonmonotone terms (slow group), special inner terms in integrated-rectifier mode."""
+    X = synthetic_samples(400, 2, seed=4) * 0.6
+    kw_std = dict(standardize_samples=False)      # keep |x| < ~2 so that order-14 terms stay O(1e3)
+    X = np.clip(X, -1.6, 1.6)
+    mon = [[[0] * o + ['HF'] for o in range(1, 8)] + ['iRBF 0', 'RBF 0'],
+           [[1] * o for o in (1, 2, 5, 9, 14)] + [[0, 1, 1, 'HF'], 'LET 1', 'iRBF 1', 'RET 1']]
+    non = [[[]], [[], [0], [0], [0] * 9 + ['HF'], [0] * 9, [0] * 4, 'RBF 0']]
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='integrated rectifier', polynomial_type=family, **kw_std)
+    tm = make_cuda(X.copy(), quadrature_input={'order': 20}, **kw)
+    om = make_oracle(X.copy(), quadrature_input={'order': 20}, **kw)
+    for k in range(2):
+        assert rel_err(tm.Psi_mon[k], om.Psi_mon[k]) <= 1e-10 and rel_err(tm.Psi_nonmon[k], om.Psi_nonmon[k]) <= 1e-10
+    rng = np.random.default_rng(1)
+    for k in range(2):
+        div = len(tm.coeffs_nonmon[k])
+        # coefficients scaled by the column magnitudes so that the rectifier argument stays O(1)
+        mag = np.concatenate((np.abs(om.Psi_nonmon[k]).max(axis=0), np.abs(om.Psi_mon[k]).max(axis=0)))
+        c = rng.standard_normal(div + len(tm.coeffs_mon[k])) * 0.2 / np.maximum(mag, 1.0)
+        J, Jo = tm.objective_function(c, k, div), om.objective_function(c, k, div)
+        assert np.isfinite(Jo) and abs(J - Jo) <= 1e-9 * max(1, abs(Jo))
+        g, go = tm.objective_function_jacobian(c, k, div), om.objective_function_jacobian(c, k, div)
+        assert np.max(np.abs(g - go) / np.maximum(1.0, np.abs(go))) <= 1e-9
+        tm.coeffs_nonmon[k], tm.coeffs_mon[k] = c[:div].copy(), c[div:].copy()
+        om.coeffs_nonmon[k], om.coeffs_mon[k] = c[:div].copy(), c[div:].copy()
+    assert rel_err(tm.map(), om.map()) <= 1e-9
+
+
+def test_order_above_compiled_limit_raises():
+    X = synthetic_samples(64, 1, seed=1)
+    tm = make_cuda(X, monotone=[[[0] * 21]], nonmonotone=[[[]]], monotonicity='integrated rectifier',
+                   quadrature_input={'order': 8})
+    with pytest.raises(RuntimeError, match='compiled limits'):
+        tm.objective_function(np.zeros(2), 0, 1)
+
+
+def test_reset_changes_ensemble_size_and_special_terms():
+    mon, non = ex05_terms()
+    X1, X2 = synthetic_samples(500, 2, seed=1), synthetic_samples(1300, 2, seed=2) * 2 + 1
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+    tm, om = make_cuda(X1.copy(), **kw), make_oracle(X1.copy(), **kw)
+    tm.optimize(); om.optimize()
+    tm.reset(X2.copy()); om.reset(X2.copy())
+    assert all(np.all(c == 0) for c in tm.coeffs_mon)
+    for k in range(2):
+        assert rel_err(tm.Psi_mon[k], om.Psi_mon[k]) <= 1e-10
+        assert rel_err(tm.der_Psi_mon[k], om.der_Psi_mon[k]) <= 1e-10
+    tm.optimize(); om.optimize()
+    for k in range(2):
+        assert rel_err(tm.coeffs_mon[k], om.coeffs_mon[k]) <= 1e-6
+        assert rel_err(tm.coeffs_nonmon[k], om.coeffs_nonmon[k]) <= 1e-6
+    Xe = synthetic_samples(77, 2, seed=3)
+    assert rel_err(tm.evaluate_pullback_density(Xe.copy()), om.evaluate_pullback_density(Xe.copy())) <= 1e-9
+
+
+def test_public_attributes_and_callables_match_reference_surface():
+    X = synthetic_samples(200, 2, seed=6)
+    mon, non = ex05_terms()
+    tm = make_cuda(X.copy(), monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+    om = make_oracle(X.copy(), monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+    assert tm.D == 2 and tm.skip_dimensions == 0 and tm.X.shape == (200, 2)
+    assert rel_err(tm.X, om.X) <= 1e-13 and rel_err(tm.X_mean, om.X_mean) <= 1e-13 and rel_err(tm.X_std, om.X_std) <= 1e-13
+    assert set(tm.special_terms[1][1].keys()) == {'counter', 'centers', 'scales'}
+    assert rel_err(tm.special_terms[1][1]['centers'], om.special_terms[1][1]['centers']) <= 1e-12
+    Xq = synthetic_samples(50, 2, seed=7)
+    assert rel_err(tm.fun_mon[1](Xq, tm), om.fun_mon(1, Xq)) <= 1e-10            # reference call signature f(x, self)
+    assert rel_err(tm.fun_nonmon[1](Xq, tm), om.fun_nonmon(1, Xq)) <= 1e-10
+    assert rel_err(tm.der_fun_mon[1](Xq, tm), om.der_fun_mon(1, Xq)) <= 1e-10
+    assert rel_err(tm.s(Xq, 1), om.s(Xq, 1)) <= 1e-10
+    assert np.array_equal(tm.optimization_constraints_lb[0], om.optimization_constraints_lb[0])
