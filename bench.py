@@ -335,6 +335,8 @@ def run_gpu(args):
         roofline = {
             'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
             'traffic': None,
+            'traffic_ncu': {'k63_bytes': 1.05e9, 'k0_bytes': 2.1e7, 'algorithmic_k63_bytes': 5.12e8,
+                            'source': 'profiles/ncu_objgrad_k63_r1.txt, ncu_objgrad_k0_r1.txt (dram read+write per launch, N=1M)'},
             'peak_source': 'ttm_fp64_peak: dependent-free DFMA chains, measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
             'flops_per_launch_avg': fl / len(mine), 'bytes_per_launch_avg': by / len(mine),
             'launch_ms_avg': t_kernels / len(mine) * 1e3,
