@@ -79,7 +79,7 @@ out['sepobj'] = {'ms': t * 1e3, 'GBps': 8 * N / t / 1e9, 'GFLOPs': 190.0 * N / t
 ng = int(os.environ.get('TTM_NGRAM', 100_000))
 G = tm._empty(M, M)
 Mp = (M + 7) // 8 * 8
-need = Mp * Mp * tm._sm_count
+need = 64 * Mp * Mp + min(ng, 1 << 18) * Mp
 if tm._scratch.numel() < need:
     tm._scratch = tm._empty(need)
 t = timeit(lambda: B.check(lib.ttm_gram(tm._plans[k], Xp, ld, ng, B.c_void_p(G.data_ptr()),

@@ -38,6 +38,9 @@ cudaError_t ttm_launch_transpose_back(const double* Xt, int64_t ld, int64_t N, i
 cudaError_t ttm_launch_basis(const PlanView& P, int which, const double* Xt, int64_t ld, int64_t N, double* Psi,
                              cudaStream_t st);
 
+cudaError_t ttm_launch_basis_concat(const PlanView& P, const double* Xt, int64_t ld, int64_t n, double* Psi,
+                                    int64_t ldp, cudaStream_t st);
+
 // separable-monotonicity evaluation: S_k and d_k S_k per sample (reference: s :2550-2558, densities :2620-2641)
 cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* coeffs,
                                 double* S_out, const double* Xd, int64_t ldd, double* dS_out, cudaStream_t st);

@@ -105,7 +105,7 @@ constexpr int T_BAS = 128, TJ_BAS = 16;
 
 __global__ void __launch_bounds__(T_BAS) basis_kernel(const PlanView P, int o_ptr, int o_fac, int m,
                                                       const double* __restrict__ Xt, int64_t ld, int64_t N,
-                                                      double* __restrict__ Psi) {
+                                                      double* __restrict__ Psi, int64_t ldp, int coff) {
     __shared__ double tile[TJ_BAS][T_BAS + 1];
     const int64_t base = (int64_t)blockIdx.x * T_BAS;
     const int64_t i = base + threadIdx.x;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(T_BAS) basis_kernel(const PlanView P, int o_pt
         __syncthreads();
         for (int e = threadIdx.x; e < w * T_BAS; e += T_BAS) {
             const int s = e / w, t = e - s * w;
-            if (base + s < N) Psi[(base + s) * (int64_t)m + j0 + t] = tile[t][s];
+            if (base + s < N) Psi[(base + s) * ldp + coff + j0 + t] = tile[t][s];
         }
         __syncthreads();
     }
@@ -175,7 +175,19 @@ cudaError_t ttm_launch_basis(const PlanView& P, int which, const double* Xt, int
     else if (which == 1) { o_ptr = P.o_mon_ptr; o_fac = P.o_mon_fac; m = P.m_mon; }
     else { o_ptr = P.o_dmon_ptr; o_fac = P.o_dmon_fac; m = P.m_dmon; }
     if (m == 0 || N == 0) return cudaSuccess;
-    basis_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, 0, st>>>(P, o_ptr, o_fac, m, Xt, ld, N, Psi);
+    basis_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, 0, st>>>(P, o_ptr, o_fac, m, Xt, ld, N, Psi, m, 0);
+    return cudaGetLastError();
+}
+
+// [Psi_non | Psi_mon] of samples [0, n) of Xt into a row-major buffer with row stride ldp (columns >= M untouched)
+cudaError_t ttm_launch_basis_concat(const PlanView& P, const double* Xt, int64_t ld, int64_t n, double* Psi,
+                                    int64_t ldp, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + T_BAS - 1) / T_BAS);
+    if (P.m_non > 0)
+        basis_kernel<<<grid, T_BAS, 0, st>>>(P, P.o_non_ptr, P.o_non_fac, P.m_non, Xt, ld, n, Psi, ldp, 0);
+    if (P.m_mon > 0)
+        basis_kernel<<<grid, T_BAS, 0, st>>>(P, P.o_mon_ptr, P.o_mon_fac, P.m_mon, Xt, ld, n, Psi, ldp, P.m_non);
     return cudaGetLastError();
 }
 

@@ -1,4 +1,4 @@
-// Separable-monotonicity kernels: K-sep-eval (S_k, d_k S_k), K-gram (DMMA), K-sepobj.
+// Separable-monotonicity kernels: K-sep-eval (S_k, d_k S_k), K-sepobj, density bookkeeping (K-gram: ttm_gram.cu).
 //
 // Reference: s (separable arm) transport_map.py:2550-2558; log-determinants :2618-2641, :2686-2709;
 // worker_task_monotone :2903-3172 (Gram-type contractions :2966-2975, :3031-3050; reduced objective
@@ -62,98 +62,6 @@ __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const
                 if (ok[r]) dS_out[idx[r]] = dS[r];
         }
     }
-}
-
-// -------------------------------------------------------------------------------------------------
-// K-gram: G = Psi^T Psi with Psi = [Psi_non | Psi_mon] (N x M), generated on the fly per sample tile
-// (no HBM round trip of Psi) and contracted with FP64 tensor-core DMMA (mma.sync m8n8k4).
-// tcgen05 has no f64 kind, so this legacy-style warp MMA is the sm_100a tensor path for FP64.
-// Each block owns a range of samples and the full M x M output; partial Grams are written to
-// scratch[block] and summed in fixed block order by gram_reduce_kernel (deterministic).
-// -------------------------------------------------------------------------------------------------
-constexpr int G_KS = 32;   // samples per staged tile
-constexpr int T_GRAM = 256;
-
-__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-// Mp = M rounded up to a multiple of 8.  smem tile: [G_KS][Mp+?]
-__global__ void __launch_bounds__(T_GRAM) gram_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
-                                                      int64_t N, double* __restrict__ scratch, int Mp) {
-    extern __shared__ double tile[];  // [G_KS][Mp + 4]
-    const int M = P.m_non + P.m_mon;
-    const int ldt = Mp + 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T_GRAM / 32;
-    const int nt = Mp / 8;                 // 8x8 output tiles per dimension
-    const int ntile = nt * (nt + 1) / 2;   // upper triangle (tj >= ti)
-    // accumulators: each warp owns tiles w, w+nwarp, ... (<= MAXT per warp, else loop in passes)
-    constexpr int MAXT = 24;
-    const int64_t chunk = (N + gridDim.x - 1) / gridDim.x;
-    const int64_t s_lo = (int64_t)blockIdx.x * chunk;
-    const int64_t s_hi = (s_lo + chunk < N) ? s_lo + chunk : N;
-    double* out = scratch + (int64_t)blockIdx.x * Mp * Mp;
-
-    for (int pass0 = 0; pass0 < ntile; pass0 += nwarp * MAXT) {
-        double c0[MAXT], c1[MAXT];
-#pragma unroll
-        for (int q = 0; q < MAXT; ++q) c0[q] = c1[q] = 0.0;
-        for (int64_t s0 = s_lo; s0 < s_hi; s0 += G_KS) {
-            __syncthreads();
-            // stage Psi rows s0..s0+G_KS-1: thread (s, j-stride)
-            for (int e = threadIdx.x; e < G_KS * Mp; e += T_GRAM) {
-                const int s = e % G_KS, j = e / G_KS;
-                double v = 0.0;
-                const int64_t i = s0 + s;
-                if (i < s_hi && j < M)
-                    v = (j < P.m_non) ? plan_term(P, P.o_non_ptr, P.o_non_fac, j, Xt, ld, i)
-                                      : plan_term(P, P.o_mon_ptr, P.o_mon_fac, j - P.m_non, Xt, ld, i);
-                tile[s * ldt + j] = v;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < MAXT; ++q) {
-                const int t = pass0 + warp + q * nwarp;
-                if (t < ntile) {
-                    // unrank upper-triangular tile index t -> (ti, tj), tj >= ti
-                    int ti = 0, rem = t;
-                    while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
-                    const int tj = ti + rem;
-                    const int arow = ti * 8 + (lane >> 2), bcol = tj * 8 + (lane >> 2), kk = lane & 3;
-#pragma unroll
-                    for (int k0 = 0; k0 < G_KS; k0 += 4)
-                        dmma_m8n8k4(c0[q], c1[q], tile[(k0 + kk) * ldt + arow], tile[(k0 + kk) * ldt + bcol]);
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < MAXT; ++q) {
-            const int t = pass0 + warp + q * nwarp;
-            if (t < ntile) {
-                int ti = 0, rem = t;
-                while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
-                const int tj = ti + rem;
-                const int row = ti * 8 + (lane >> 2), col = tj * 8 + 2 * (lane & 3);
-                out[(int64_t)row * Mp + col] = c0[q];
-                out[(int64_t)row * Mp + col + 1] = c1[q];
-            }
-        }
-    }
-}
-
-// G[i][j] = sum_b scratch[b][min][max] (fixed order), symmetric fill, M x M output
-__global__ void gram_reduce_kernel(const double* __restrict__ scratch, int nblocks, int Mp, int M,
-                                   double* __restrict__ G) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= M * M) return;
-    const int i = e / M, j = e % M;
-    const int r = min(i, j), c = max(i, j);
-    // element (r, c) lives in tile (r/8, c/8) with tj >= ti: always stored
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += scratch[(int64_t)b * Mp * Mp + (int64_t)r * Mp + c];
-    G[e] = s;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -253,27 +161,6 @@ cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld,
         if (e != cudaSuccess) return e;
     }
     sep_eval_kernel<<<(unsigned)grid, T_SEP, smem, st>>>(P, Xt, ld, N, coeffs, S_out, Xd, ldd, dS_out);
-    return cudaGetLastError();
-}
-
-cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch,
-                            int64_t scratch_doubles, int sm_count, cudaStream_t st) {
-    const int M = P.m_non + P.m_mon;
-    if (M == 0) return cudaSuccess;
-    const int Mp = (M + 7) / 8 * 8;
-    int64_t grid = scratch_doubles / ((int64_t)Mp * Mp);
-    if (grid > sm_count) grid = sm_count;
-    const int64_t max_by_n = (N + G_KS - 1) / G_KS;
-    if (grid > max_by_n) grid = max_by_n;
-    if (grid < 1) return cudaErrorInvalidValue;
-    const size_t smem = sizeof(double) * (size_t)G_KS * (Mp + 4);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    gram_kernel<<<(unsigned)grid, T_GRAM, smem, st>>>(P, Xt, ld, N, scratch, Mp);
-    gram_reduce_kernel<<<(M * M + 255) / 256, 256, 0, st>>>(scratch, (int)grid, Mp, M, G);
     return cudaGetLastError();
 }
 

@@ -589,7 +589,7 @@ class transport_map():
         M = p.m_non + p.m_mon
         G = self._empty(M, M)
         Mp = (M + 7) // 8 * 8
-        need = Mp * Mp * min(self._sm_count, max(1, (self._N + 31) // 32))
+        need = 64 * Mp * Mp + min(self._N, 1 << 18) * Mp      # split partials + one materialised Psi chunk
         if self._scratch.numel() < need:
             self._scratch = self._empty(need)
         B.check(self._lib.ttm_gram(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1], self._N,
