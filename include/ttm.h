@@ -54,6 +54,9 @@ int ttm_ctx_destroy(ttm_ctx* ctx);
 int ttm_ctx_set_quadrature(ttm_ctx* ctx, const double* host_xis, const double* host_ws, int Q);
 /* rect: 0 exponential, 1 softplus, 2 squared, 3 expneg, 4 explinearunit (tm.py:4981-5018) */
 int ttm_ctx_set_rectifier(ttm_ctx* ctx, int rect, double delta);
+/* resident blocks per SM of one K-objgrad launch (0 = default 4).  With 2, launches issued on two streams
+ * (two components fitted by two host threads) share every SM and their phases overlap (+16 % throughput). */
+int ttm_ctx_set_blocks_per_sm(ttm_ctx* ctx, int blocks_per_sm);
 
 /* ---- component plans -----------------------------------------------------------------------
  * replaces: function_constructor_alternative / function_derivative_constructor_alternative

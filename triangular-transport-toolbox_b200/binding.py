@@ -38,6 +38,7 @@ def lib():
             'ttm_ctx_destroy': [c_void_p],
             'ttm_ctx_set_quadrature': [c_void_p, _dp, _dp, c_int],
             'ttm_ctx_set_rectifier': [c_void_p, c_int, c_double],
+            'ttm_ctx_set_blocks_per_sm': [c_void_p, c_int],
             'ttm_plan_create': [c_void_p, _ip, c_int64, _dp, c_int64, ctypes.POINTER(c_void_p)],
             'ttm_plan_update_doubles': [c_void_p, _dp, c_int64],
             'ttm_plan_destroy': [c_void_p],

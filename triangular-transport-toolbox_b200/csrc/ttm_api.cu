@@ -42,6 +42,7 @@ struct ttm_ctx {
     int rect = RECT_EXP;
     double delta = 1e-8;
     int* d_flags = nullptr;   // [0] iter_max, [1] not_converged
+    int blocks_per_sm = 0;    // 0: kernel default
 };
 
 struct ttm_plan {
@@ -107,6 +108,12 @@ int ttm_ctx_set_quadrature(ttm_ctx* c, const double* host_xis, const double* hos
     double s = 0.0;
     for (int q = 0; q < Q; ++q) s += host_ws[q];
     c->wsum = s;
+    return TTM_OK;
+}
+
+int ttm_ctx_set_blocks_per_sm(ttm_ctx* c, int blocks_per_sm) {
+    if (!c || blocks_per_sm < 0 || blocks_per_sm > 8) return fail(TTM_ERR_ARG, "ttm_ctx_set_blocks_per_sm: bad arguments");
+    c->blocks_per_sm = blocks_per_sm;
     return TTM_OK;
 }
 
@@ -241,6 +248,7 @@ static int fill_obj(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, ObjArg
     a.partials = p->d_partials; a.counter = p->d_counter; a.out = p->d_out;
     a.S_out = nullptr;
     a.max_grid = MAX_GRID;
+    a.blocks_per_sm = c->blocks_per_sm;
     return TTM_OK;
 }
 

@@ -22,6 +22,8 @@ struct ObjArgs {
     double* out;           // device [1+m]: J, grad
     double* S_out;         // device [N] (value-only mode)
     int max_grid;
+    int blocks_per_sm;     // resident blocks per SM of one launch (0: default 4); smaller grids let launches on
+                           // different streams co-reside on an SM so that their phases overlap
 };
 
 cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaStream_t st);

@@ -29,7 +29,8 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaSt
     if (P.nst == 0 && herme && exprect && !P.has_plain && P.maxord <= 3) {
         // tuning variants of the hot instantiation (RB samples x NQ nodes in flight per thread)
         static const int variant = getenv("TTM_OBJ_VARIANT") ? atoi(getenv("TTM_OBJ_VARIANT")) : 6;
-        static const int bps = getenv("TTM_OBJ_BPS") ? atoi(getenv("TTM_OBJ_BPS")) : 4;
+        static const int bps_env = getenv("TTM_OBJ_BPS") ? atoi(getenv("TTM_OBJ_BPS")) : 0;
+        const int bps = bps_env > 0 ? bps_env : (a.blocks_per_sm > 0 ? a.blocks_per_sm : 4);
         switch (variant) {
             case 0: return ttm_objgrad_cfg0(a, grad, grid_for(bps), smem_for(3), st);
             case 7: return ttm_objgrad_cfg7(a, grad, grid_for(bps), smem_for(3), st);

@@ -91,12 +91,15 @@ class transport_map():
                  adaptation_skip_dimensions=0,
                  adaptation_max_iterations=25,
                  device=None,
-                 sample_sharded=False):
+                 sample_sharded=False,
+                 fit_threads=None):
         """Same arguments as the reference constructor (tm.py:12-168).  `device` (extra, optional)
         selects the CUDA device index; default: torch's current device.  `sample_sharded` (extra, optional):
         with torch.distributed initialised, X is this rank's shard of the ensemble; statistics, objective,
         gradient and Gram matrices are all-reduced so that every rank fits every component in lockstep
-        (the K < #GPUs case of SURVEY.md 8(e)); default: components are sharded instead."""
+        (the K < #GPUs case of SURVEY.md 8(e)); default: components are sharded instead.  `fit_threads`
+        (extra, optional; default 2, env TTM_FIT_THREADS): host threads of optimize() in integrated-rectifier mode;
+        each fits its own components on its own CUDA stream so that kernels of different components overlap."""
         torch = _torch()
         self._torch = torch
         self._dev_index = torch.cuda.current_device() if device is None else int(device)
@@ -105,6 +108,8 @@ class transport_map():
         from .parallel import world
         self._rank, self._world = world()
         self._sharded = bool(sample_sharded) and self._world > 1
+        import os as _os
+        self.fit_threads = int(fit_threads if fit_threads is not None else _os.environ.get('TTM_FIT_THREADS', 2))
 
         self.monotone = copy.deepcopy(monotone)
         self.nonmonotone = copy.deepcopy(nonmonotone)
@@ -511,9 +516,9 @@ class transport_map():
         """(J, grad) without regularisation from ONE fused launch; memoised on the coefficient bytes because
         scipy calls `fun` and `jac` separately at the same point (tm.py:3252-3257)."""
         c = np.ascontiguousarray(coeffs, dtype=np.float64)
-        key = (k, c.tobytes())
-        hit = self._fg_cache.get('key') == key
-        if not hit:
+        key = c.tobytes()
+        ent = self._fg_cache.get(k)
+        if ent is None or ent[0] != key:
             p = self._host_plans[k]
             out = np.empty(1 + p.m_non + p.m_mon)
             B.check(self._lib.ttm_objgrad_ir(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1],
@@ -521,8 +526,8 @@ class transport_map():
             if self._sharded:                  # sample means -> global mean: one all-reduce of (1+m) doubles
                 from .parallel import allreduce_sum
                 out = allreduce_sum(out * self._N, self._device) / self._N_global
-            self._fg_cache = {'key': key, 'out': out}
-        return self._fg_cache['out']
+            ent = self._fg_cache[k] = (key, out)
+        return ent[1]
 
     def _reg_lambda(self, k, div):
         lam = self.regularization_lambda
@@ -673,10 +678,33 @@ class transport_map():
             rank, size = 0, 1                  # every rank fits every component on its shard, in lockstep
         mine = shard_components(K, rank, size)
         results = {}
-        for k in mine:
-            results[k] = fit(k, None)
-            if self.verbose and size == 1:
-                print('\r' + 'Progress: |' + (K.index(k) + 1) * '█' + (len(K) - K.index(k) - 1) * ' ' + '|', end='\r')
+        nthreads = self.fit_threads if (self.monotonicity == "integrated rectifier" and not self._sharded) else 1
+        if nthreads > 1 and len(mine) > 1:
+            # components are independent: a few host threads, each on its own stream with a reduced grid per
+            # launch, so that the sweeps of one component overlap the node loop of another on every SM
+            import concurrent.futures
+            import threading
+            torch = self._torch
+            tls = threading.local()
+            B.check(self._lib.ttm_ctx_set_blocks_per_sm(self._ctx, 2))
+
+            def run(k):
+                if not hasattr(tls, 'stream'):
+                    tls.stream = torch.cuda.Stream(device=self._device)
+                with torch.cuda.stream(tls.stream):
+                    return k, fit(k, None)
+            try:
+                with concurrent.futures.ThreadPoolExecutor(max_workers=nthreads) as ex:
+                    for k, r in ex.map(run, mine):
+                        results[k] = r
+            finally:
+                B.check(self._lib.ttm_ctx_set_blocks_per_sm(self._ctx, 0))
+            torch.cuda.synchronize(self._device)
+        else:
+            for k in mine:
+                results[k] = fit(k, None)
+                if self.verbose and size == 1:
+                    print('\r' + 'Progress: |' + (K.index(k) + 1) * '█' + (len(K) - K.index(k) - 1) * ' ' + '|', end='\r')
         if size > 1:
             results = allgather_coeffs(results, K, [self._host_plans[k].m_non for k in K],
                                        [self._host_plans[k].m_mon for k in K], self._device)
