@@ -240,6 +240,7 @@ def run_gpu(args):
     lib, stream = tm._lib, tm._stream()
     Xp, ld = B.c_void_p(tm._Xt.data_ptr()), tm._Xt.shape[1]
     for k in mine:
+        tm._gram_nonmon(k)                          # no-op unless TTM_GRAM=1 (experimental one-sweep kernel)
         tm._set_coeffs(k, coefs[k][:len(non[k])], coefs[k][len(non[k]):])
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')   # 512 MB > 126 MB L2
 

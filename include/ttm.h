@@ -91,6 +91,11 @@ int ttm_basis_eval(ttm_plan* plan, int which, const double* Xt, int64_t ld, int6
  * host_coeffs = [coeffs_nonmon | coeffs_mon] (m doubles); host_out = [J, dJ/dcoeffs] (1+m doubles),
  * WITHOUT the regularisation terms (the host adds them, tm.py:3382-3431 / :3575-3633).
  * ttm_objgrad_ir = set_coeffs + launch + get_out (synchronises `stream`).                        */
+/* Gram mode: dJ/da = G a + h with G = Psi_non^T Psi_non / N (ttm_gram, once per ensemble, like the reference's
+ * precalculate()).  When on, the nonmonotone slots of host_out hold h_j = mean_i M_i psi_ij only and the caller
+ * adds G a; the kernel then needs one sweep over the columns x_<c instead of two.  Fails with TTM_ERR_LIMIT if
+ * a nonmonotone polynomial order exceeds 3. */
+int ttm_plan_set_gram_mode(ttm_plan* plan, int on);
 int ttm_plan_set_coeffs(ttm_plan* plan, const double* host_coeffs, void* stream);
 int ttm_objgrad_ir_launch(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, void* stream);
 int ttm_plan_get_out(ttm_plan* plan, double* host_out, int n, void* stream);

@@ -130,3 +130,30 @@ def test_public_attributes_and_callables_match_reference_surface():
     assert rel_err(tm.der_fun_mon[1](Xq, tm), om.der_fun_mon(1, Xq)) <= 1e-10
     assert rel_err(tm.s(Xq, 1), om.s(Xq, 1)) <= 1e-10
     assert np.array_equal(tm.optimization_constraints_lb[0], om.optimization_constraints_lb[0])
+
+
+def test_gram_mode_equals_two_sweep_kernel_and_oracle():
+    """dJ/da = G a + h (one sweep, Gram precomputed) against the two-sweep kernel and the oracle, incl. partial maps,
+    ragged N and a component mixing dense, special and multivariate nonmonotone terms."""
+    from cases import ex06_terms
+    X = synthetic_samples(3001, 5, seed=12)
+    mon, non = c4_terms(5)
+    non[4] = non[4] + ['RBF 1', [0, 2], [3], [3]]            # special, multivariate, duplicate terms
+    mon2 = [[[k + 1, 'HF'], [k + 1, k + 1, 'HF'], [k, k + 1, 'HF']] for k in range(4)]
+    non2 = [[[]] + [[j] for j in range(k + 1)] + [[j, j, 'HF'] for j in range(k + 1)] for k in range(4)]
+    for (mo, no) in ((mon, non), (mon2, non2)):
+        kw = dict(monotone=mo, nonmonotone=no, monotonicity='integrated rectifier')
+        tg = make_cuda(X.copy(), quadrature_input={'order': 15}, **kw)
+        tg._use_gram = True
+        t2 = make_cuda(X.copy(), quadrature_input={'order': 15}, **kw)
+        t2._use_gram = False
+        om = make_oracle(X.copy(), quadrature_input={'order': 15}, **kw)
+        rng = np.random.default_rng(3)
+        for k in range(tg.D):
+            div = len(tg.coeffs_nonmon[k])
+            c = rng.standard_normal(div + len(tg.coeffs_mon[k])) * 0.2
+            Jg, J2, Jo = (t.objective_function(c, k, div) for t in (tg, t2, om))
+            gg, g2, go = (t.objective_function_jacobian(c, k, div) for t in (tg, t2, om))
+            assert tg._gram_nn[k] is not None and t2._gram_nn[k] is None
+            assert abs(Jg - Jo) <= 1e-10 * max(1, abs(Jo)) and abs(J2 - Jo) <= 1e-10 * max(1, abs(Jo))
+            assert rel_err(gg, go) <= 1e-10 and rel_err(g2, go) <= 1e-10

@@ -24,6 +24,7 @@ tm = transport_map(X=X, monotone=mon, nonmonotone=non, monotonicity='integrated 
 rng = np.random.default_rng(0)
 coefs = [rng.standard_normal(len(non[k]) + len(mon[k])) * 0.05 for k in range(D)]
 for k in range(D):
+    tm._gram_nonmon(k)
     tm._set_coeffs(k, coefs[k][:len(non[k])], coefs[k][len(non[k]):])
 torch.cuda.synchronize()
 streams = [torch.cuda.Stream() for _ in range(nstreams)]

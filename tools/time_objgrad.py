@@ -27,6 +27,7 @@ out = {'variant': os.environ.get('TTM_OBJ_VARIANT', '0'), 'bps': os.environ.get(
 stream = tm._stream()
 Xp, ld = B.c_void_p(tm._Xt.data_ptr()), tm._Xt.shape[1]
 for k in (0, 1, 31, 63):
+    tm._gram_nonmon(k)
     tm._set_coeffs(k, coefs[k][:len(non[k])], coefs[k][len(non[k]):])
     for _ in range(3):
         B.check(tm._lib.ttm_objgrad_ir_launch(tm._plans[k], Xp, ld, n, stream))

@@ -48,6 +48,7 @@ def lib():
             'ttm_transpose_back': [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_void_p],
             'ttm_basis_eval': [c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
+            'ttm_plan_set_gram_mode': [c_void_p, c_int],
             'ttm_plan_set_coeffs': [c_void_p, _dp, c_void_p],
             'ttm_objgrad_ir_launch': [c_void_p, c_void_p, c_int64, c_int64, c_void_p],
             'ttm_plan_get_out': [c_void_p, _dp, c_int, c_void_p],

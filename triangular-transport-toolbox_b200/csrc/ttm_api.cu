@@ -57,6 +57,7 @@ struct ttm_plan {
     double* d_partials = nullptr;  // [MAX_GRID][1+m]
     unsigned int* d_counter = nullptr;
     double* h_pin = nullptr;       // pinned staging [2*(1+m)]
+    int gram_mode = 0;
 };
 
 extern "C" {
@@ -142,7 +143,7 @@ static int parse_view(ttm_plan* p, const int32_t* h) {
     v.o_ent_i = h[H_ENT_I]; v.o_multi_idx = h[H_MULTI_IDX];
     v.o_slot_ptr = h[H_SLOT_PTR]; v.o_slot_term = h[H_SLOT_TERM];
     v.o_out_ptr = h[H_OUT_PTR]; v.o_out_fac = h[H_OUT_FAC]; v.o_st_fac = h[H_ST_FAC];
-    v.ndense = h[H_NDENSE]; v.dense_maxord = h[H_DENSE_MAXORD];
+    v.ndense = h[H_NDENSE]; v.dense_maxord = h[H_DENSE_MAXORD]; v.nactive = h[H_NACTIVE];
     v.o_dense_var = h[H_DENSE_VAR]; v.o_dense_idx = h[H_DENSE_IDX]; v.o_d_dense_scale = h[H_D_DENSE_SCALE];
     v.o_d_fac = h[H_D_FAC]; v.o_d_ent = h[H_D_ENT]; v.o_d_slot_scale = h[H_D_SLOT_SCALE]; v.o_d_rec = h[H_D_REC];
     // alignment of the vector-loaded records
@@ -226,6 +227,14 @@ int ttm_basis_eval(ttm_plan* p, int which, const double* Xt, int64_t ld, int64_t
     return TTM_OK;
 }
 
+int ttm_plan_set_gram_mode(ttm_plan* p, int on) {
+    if (!p) return fail(TTM_ERR_ARG, "ttm_plan_set_gram_mode: null plan");
+    if (on && p->view.dense_maxord > 3)
+        return fail(TTM_ERR_LIMIT, "ttm_plan_set_gram_mode: nonmonotone polynomial order > 3 needs the two-sweep kernel");
+    p->gram_mode = on ? 1 : 0;
+    return TTM_OK;
+}
+
 int ttm_plan_set_coeffs(ttm_plan* p, const double* host_coeffs, void* stream) {
     if (!p || !host_coeffs) return fail(TTM_ERR_ARG, "ttm_plan_set_coeffs: null argument");
     if (p->m == 0) return TTM_OK;
@@ -249,6 +258,8 @@ static int fill_obj(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, ObjArg
     a.S_out = nullptr;
     a.max_grid = MAX_GRID;
     a.blocks_per_sm = c->blocks_per_sm;
+    a.gram_mode = p->gram_mode;
+    a.ch_rows = 0;
     return TTM_OK;
 }
 

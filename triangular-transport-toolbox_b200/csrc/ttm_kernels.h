@@ -22,6 +22,8 @@ struct ObjArgs {
     double* out;           // device [1+m]: J, grad
     double* S_out;         // device [N] (value-only mode)
     int max_grid;
+    int gram_mode;         // 1: nonmonotone gradient slots return h_j = sum_i M_i psi_ij / N (host adds G a)
+    int ch_rows;           // rows per chunk (set by the dispatcher)
     int blocks_per_sm;     // resident blocks per SM of one launch (0: default 4); smaller grids let launches on
                            // different streams co-reside on an SM so that their phases overlap
 };

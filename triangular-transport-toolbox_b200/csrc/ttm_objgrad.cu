@@ -6,9 +6,13 @@
 
 // Returns cudaErrorInvalidValue if the plan exceeds the compiled limits (order > 20 or > 8
 // special-term inner factors).
-cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaStream_t st) {
+cudaError_t ttm_launch_objgrad(const ObjArgs& a_in, bool grad, int sm_count, cudaStream_t st) {
     using ttm_obj::T_OBJ;
+    ObjArgs a = a_in;
     const PlanView& P = a.P;
+    if (!grad) a.gram_mode = 0;
+    if (a.gram_mode && P.dense_maxord > 3) return cudaErrorInvalidValue;   // merged sweep handles orders <= 3
+    a.ch_rows = a.gram_mode ? 2 * ttm_obj::RC_SWEEP : ttm_obj::CH_ROWS;
     const int m = P.m_non + P.m_mon;
     const bool herme = (P.family == FAM_HERMITE_E);
     const bool exprect = (a.rect == RECT_EXP);
@@ -18,7 +22,7 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaSt
         return sizeof(double) * (size_t)(m + 2 * (a.Q + 4) + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0) +
                                         (size_t)P.ndense * 2 * (P.dense_maxord + 1) * 2 + 2 * P.ndense + 6) +
                sizeof(int) * (size_t)(P.ndense * 2 * (P.dense_maxord + 1) + 8) +
-               sizeof(double) * (size_t)(ttm_obj::CH_ROWS * T_OBJ + 2);
+               sizeof(double) * ((size_t)a.ch_rows * T_OBJ * (1 + (a.gram_mode ? 1 + P.nactive : 0)) + 2);
     };
     auto grid_for = [&](int blocks_per_sm) {
         int64_t g = (int64_t)sm_count * blocks_per_sm;

@@ -140,35 +140,54 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     const int64_t rows = (N + T_OBJ - 1) / T_OBJ;
     const int64_t row_lo = rows * blockIdx.x / gridDim.x, row_hi = rows * (blockIdx.x + 1) / gridDim.x;
 
-    for (int64_t chunk_lo = row_lo; chunk_lo < row_hi; chunk_lo += CH_ROWS) {
-    const int64_t chunk_hi = (chunk_lo + CH_ROWS < row_hi) ? chunk_lo + CH_ROWS : row_hi;
-    // ---------------- phase A, dense groups: S_non of the whole chunk -> s_S ----------------
-    for (int64_t row8 = chunk_lo; row8 < chunk_hi; row8 += RC_SWEEP) {
-        bool okr[RC_SWEEP];
-        double S8[RC_SWEEP];
+    // Gram mode (GRAD only): dJ/da = G a + h with G = Psi_non^T Psi_non / N precomputed on the host side of the
+    // ABI; the kernel then needs ONE nonmonotone sweep per chunk (value and h together) instead of two:
+    //   pass 1  node loops of the chunk            -> M_i and the slot integrals I_{i,s} parked in shared memory
+    //   sweep   S_non and h_j = sum_i M_i psi_ij   (dense_merged_chunk_smem)
+    //   pass 2  epilogue: S = S_non + M, J, monotone gradient
+    // Otherwise (pass 0): phase A sweep, node loop + epilogue, phase C sweep.
+    const bool gm = GRAD && a.gram_mode != 0;
+    const int ch_rows = a.ch_rows;
+    double* s_M = s_S + ch_rows * T_OBJ;                 // [ch_rows][T_OBJ]     (gram mode)
+    double* s_I = s_M + ch_rows * T_OBJ;                 // [nactive][ch_rows][T_OBJ]
+    for (int64_t chunk_lo = row_lo; chunk_lo < row_hi; chunk_lo += ch_rows) {
+    const int64_t chunk_hi = (chunk_lo + ch_rows < row_hi) ? chunk_lo + ch_rows : row_hi;
+    if (!gm) {
+        // ---------------- phase A, dense groups: S_non of the whole chunk -> s_S ----------------
+        for (int64_t row8 = chunk_lo; row8 < chunk_hi; row8 += RC_SWEEP) {
+            bool okr[RC_SWEEP];
+            double S8[RC_SWEEP];
 #pragma unroll
-        for (int r = 0; r < RC_SWEEP; ++r) {
-            okr[r] = (row8 + r < chunk_hi) && ((row8 + r) * T_OBJ + tid < N);
-            S8[r] = 0.0;
+            for (int r = 0; r < RC_SWEEP; ++r) {
+                okr[r] = (row8 + r < chunk_hi) && ((row8 + r) * T_OBJ + tid < N);
+                S8[r] = 0.0;
+            }
+            dense_value_smem<HERME, 3, RC_SWEEP>(P, DS, Xt, ld, row8 * T_OBJ + tid, T_OBJ, okr, S8);
+#pragma unroll
+            for (int r = 0; r < RC_SWEEP; ++r)
+                if (row8 + r < chunk_hi) s_S[(row8 + r - chunk_lo) * T_OBJ + tid] = S8[r];
         }
-        dense_value_smem<HERME, 3, RC_SWEEP>(P, DS, Xt, ld, row8 * T_OBJ + tid, T_OBJ, okr, S8);
-#pragma unroll
-        for (int r = 0; r < RC_SWEEP; ++r)
-            if (row8 + r < chunk_hi) s_S[(row8 + r - chunk_lo) * T_OBJ + tid] = S8[r];
     }
+#pragma unroll 1
+    for (int pass = gm ? 1 : 0; pass <= (gm ? 2 : 0); ++pass) {
+    if (pass == 2)
+        dense_merged_chunk_smem<HERME, RC_SWEEP>(P, DS, Xt, ld, chunk_lo, chunk_hi, N, T_OBJ, tid, s_M, s_S, gslot, lane);
     for (int64_t row0 = chunk_lo; row0 < chunk_hi; row0 += R_OBJ) {
         int64_t idx[R_OBJ];
-        double valid[R_OBJ], S[R_OBJ];
+        double valid[R_OBJ], S[R_OBJ], Mv[R_OBJ];
 #pragma unroll
         for (int r = 0; r < R_OBJ; ++r) {
             const int64_t i = (row0 + r) * T_OBJ + tid;
             const bool ok = (row0 + r < chunk_hi) && (i < N);
             valid[r] = ok ? 1.0 : 0.0;
             idx[r] = ok ? i : (N - 1);
-            S[r] = (row0 + r < chunk_hi) ? s_S[(row0 + r - chunk_lo) * T_OBJ + tid] : 0.0;
+            const bool in = row0 + r < chunk_hi;
+            S[r] = (in && pass != 1) ? s_S[(row0 + r - chunk_lo) * T_OBJ + tid] : 0.0;
+            Mv[r] = (in && pass == 2) ? s_M[(row0 + r - chunk_lo) * T_OBJ + tid] : 0.0;
         }
-        // ---------------- phase A ----------------
-        nonmon_sweep<false, HERME, false>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
+        // ---------------- phase A (constants, special terms, multivariate terms) ----------------
+        if (pass != 1) nonmon_sweep<false, HERME, false>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
+        if (pass == 2) nonmon_sweep<true, HERME, false>(P, DT, Xt, ld, idx, acoef, Mv, gslot, lane);  // their h_j
 
         // ---------------- phase B ----------------
 #pragma unroll 1
@@ -249,6 +268,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
             };
 
             // ---- Gauss-Legendre node loop (transport_map.py:4252-4278) ----
+            if (pass != 2) {
             if (NST == 0) {
                 // staged ("vector") form: L = NQ x RB node-samples advance through every stage together
                 constexpr int L = NQ * RB;
@@ -311,37 +331,84 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 }
             } else {
 #pragma unroll 1
-            for (int q = 0; q < Qp; q += NQ) {
+                for (int q = 0; q < Qp; q += NQ) {
 #pragma unroll
-                for (int u = 0; u < NQ; ++u) {
-                    const double xi = s_xis[q + u], w = s_ws[q + u];
+                    for (int u = 0; u < NQ; ++u) {
+                        const double xi = s_xis[q + u], w = s_ws[q + u];
 #pragma unroll
-                    for (int rb = 0; rb < RB; ++rb) {
-                        const double t = fma(hx[rb], xi, hx[rb]);
-                        double Pl[MAXORD + 1], ga = 1.0, sv[NSTA];
-                        const double r = inner(rb, t, Pl, ga, sv);
-                        const double g = EXPRECT ? ttm_exp(r) : rect_eval(a.rect, r);
-                        Sacc[rb] = fma(w, g, Sacc[rb]);
-                        if (GRAD) {
-                            const double wd = w * (EXPRECT ? g : rect_dfac(a.rect, r, g));
-                            if (HAS_PLAIN) {
+                        for (int rb = 0; rb < RB; ++rb) {
+                            const double t = fma(hx[rb], xi, hx[rb]);
+                            double Pl[MAXORD + 1], ga = 1.0, sv[NSTA];
+                            const double r = inner(rb, t, Pl, ga, sv);
+                            const double g = EXPRECT ? ttm_exp(r) : rect_eval(a.rect, r);
+                            Sacc[rb] = fma(w, g, Sacc[rb]);
+                            if (GRAD) {
+                                const double wd = w * (EXPRECT ? g : rect_dfac(a.rect, r, g));
+                                if (HAS_PLAIN) {
 #pragma unroll
-                                for (int o = 0; o <= MAXORD; ++o) Ip[o][rb] = fma(wd, Pl[o], Ip[o][rb]);
-                            }
-                            if (HAS_HF) {
-                                const double wg = wd * ga;
+                                    for (int o = 0; o <= MAXORD; ++o) Ip[o][rb] = fma(wd, Pl[o], Ip[o][rb]);
+                                }
+                                if (HAS_HF) {
+                                    const double wg = wd * ga;
 #pragma unroll
-                                for (int o = 1; o <= MAXORD; ++o) Ih[o][rb] = fma(wg, Pl[o], Ih[o][rb]);
-                            }
-                            if (NST > 0) {
+                                    for (int o = 1; o <= MAXORD; ++o) Ih[o][rb] = fma(wg, Pl[o], Ih[o][rb]);
+                                }
+                                if (NST > 0) {
 #pragma unroll
-                                for (int qq = 0; qq < NST; ++qq) Is[qq][rb] = fma(wd, sv[qq], Is[qq][rb]);
+                                    for (int qq = 0; qq < NST; ++qq) Is[qq][rb] = fma(wd, sv[qq], Is[qq][rb]);
+                                }
                             }
                         }
                     }
                 }
             }
+            }
 
+            // slot integrals I_s into the slot-indexed staging array
+            if (GRAD && pass != 2) {
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) {
+#pragma unroll
+                    for (int o = 0; o <= MAXORD; ++o) {
+                        tmp[rb][2 * o] = HAS_PLAIN ? Ip[o][rb] : 0.0;
+                        tmp[rb][2 * o + 1] = (HAS_HF && o > 0) ? Ih[o][rb] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NST; ++q) tmp[rb][2 * (MAXORD + 1) + q] = Is[q][rb];
+                }
+            }
+            if (pass == 1) {
+                // park M_i and the integrals of the non-empty slots; the epilogue runs after the merged sweep
+                int ai = 0;
+#pragma unroll 1
+                for (int s = 0; s < nslot_rt; ++s) {
+                    if (__ldg(P.ib + P.o_slot_ptr + s) == __ldg(P.ib + P.o_slot_ptr + s + 1)) continue;
+                    const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
+#pragma unroll
+                    for (int rb = 0; rb < RB; ++rb)
+                        if (row0 + r0 + rb < chunk_hi)
+                            s_I[(ai * ch_rows + (int)(row0 + r0 + rb - chunk_lo)) * T_OBJ + tid] = tmp[rb][ts];
+                    ++ai;
+                }
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb)
+                    if (row0 + r0 + rb < chunk_hi)
+                        s_M[(row0 + r0 + rb - chunk_lo) * T_OBJ + tid] =
+                            valid[r0 + rb] * hx[rb] * fma(a.delta, a.wsum, Sacc[rb]);
+                continue;
+            }
+            if (pass == 2) {
+                int ai = 0;
+#pragma unroll 1
+                for (int s = 0; s < nslot_rt; ++s) {
+                    if (__ldg(P.ib + P.o_slot_ptr + s) == __ldg(P.ib + P.o_slot_ptr + s + 1)) continue;
+                    const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
+#pragma unroll
+                    for (int rb = 0; rb < RB; ++rb)
+                        tmp[rb][ts] = (row0 + r0 + rb < chunk_hi)
+                                          ? s_I[(ai * ch_rows + (int)(row0 + r0 + rb - chunk_lo)) * T_OBJ + tid] : 0.0;
+                    ++ai;
+                }
             }
 
             // ---- per-sample epilogue ----
@@ -349,7 +416,8 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
             double base[RB][NSLOT_T];   // slot basis values at x_c (local memory, indexed by plan slot below)
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
-                const double M = hx[rb] * fma(a.delta, a.wsum, Sacc[rb]);  // sum_q hx w_q (g_q + delta)
+                const double M = (pass == 2) ? Mv[r0 + rb]
+                                             : hx[rb] * fma(a.delta, a.wsum, Sacc[rb]);  // sum_q hx w_q (g_q + delta)
                 Sfull[rb] = S[r0 + rb] + M;
                 if (GRAD) {
                     double Plx[MAXORD + 1], gax = 1.0, svx[NSTA];
@@ -361,16 +429,11 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                     S[r0 + rb] = valid[r0 + rb] * Sfull[rb];
 #pragma unroll
                     for (int o = 0; o <= MAXORD; ++o) {
-                        tmp[rb][2 * o] = HAS_PLAIN ? Ip[o][rb] : 0.0;
-                        tmp[rb][2 * o + 1] = (HAS_HF && o > 0) ? Ih[o][rb] : 0.0;
                         base[rb][2 * o] = Plx[o];
                         base[rb][2 * o + 1] = Plx[o] * gax;
                     }
 #pragma unroll
-                    for (int q = 0; q < NST; ++q) {
-                        tmp[rb][2 * (MAXORD + 1) + q] = Is[q][rb];
-                        base[rb][2 * (MAXORD + 1) + q] = svx[q];
-                    }
+                    for (int q = 0; q < NST; ++q) base[rb][2 * (MAXORD + 1) + q] = svx[q];
                 } else {
                     S[r0 + rb] = Sfull[rb];
                 }
@@ -405,7 +468,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
 #pragma unroll
             for (int r = 0; r < R_OBJ; ++r)
                 if (valid[r] != 0.0) a.S_out[idx[r]] = S[r];
-        } else {
+        } else if (pass == 0) {
             // ---------------- phase C ----------------
             // constants / special terms / multivariate terms per row group; dense groups per chunk below
             nonmon_sweep<true, HERME, false>(P, DT, Xt, ld, idx, acoef, S, gslot, lane);
@@ -414,7 +477,8 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 if (row0 + r < chunk_hi) s_S[(row0 + r - chunk_lo) * T_OBJ + tid] = S[r];
         }
     }
-    if (GRAD)
+    }
+    if (GRAD && !gm)
         dense_grad_chunk_smem<HERME, 3, RC_SWEEP>(P, DS, Xt, ld, chunk_lo, chunk_hi, N, T_OBJ, tid, s_S, gslot, lane);
     }
 

@@ -110,6 +110,9 @@ class transport_map():
         self._sharded = bool(sample_sharded) and self._world > 1
         import os as _os
         self.fit_threads = int(fit_threads if fit_threads is not None else _os.environ.get('TTM_FIT_THREADS', 2))
+        self._use_gram = _os.environ.get('TTM_GRAM', '0') != '0'   # experimental one-sweep kernel, see DESIGN.md
+        import threading as _threading
+        self._gram_lock = _threading.Lock()
 
         self.monotone = copy.deepcopy(monotone)
         self.nonmonotone = copy.deepcopy(nonmonotone)
@@ -443,6 +446,7 @@ class transport_map():
         if self.monotonicity.lower() == 'separable monotonicity':
             self.der_Psi_mon = _LazyList(self.D, lambda k: self._basis(k, 2, self._Xt, self._N))
         self._fg_cache = {}
+        self._gram_nn = {}
 
     def reset(self, X):
         """tm.py:710-748."""
@@ -520,14 +524,36 @@ class transport_map():
         ent = self._fg_cache.get(k)
         if ent is None or ent[0] != key:
             p = self._host_plans[k]
+            G = self._gram_nonmon(k)
             out = np.empty(1 + p.m_non + p.m_mon)
             B.check(self._lib.ttm_objgrad_ir(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1],
                                              self._N, B.dptr(c), B.dptr(out), self._stream()))
             if self._sharded:                  # sample means -> global mean: one all-reduce of (1+m) doubles
                 from .parallel import allreduce_sum
                 out = allreduce_sum(out * self._N, self._device) / self._N_global
+            if G is not None:                  # Gram mode: the kernel returned h only, dJ/da = G a + h
+                out[1:1 + p.m_non] += G @ c[:p.m_non]
             ent = self._fg_cache[k] = (key, out)
         return ent[1]
+
+    def _gram_nonmon(self, k):
+        """G = Psi_non^T Psi_non / N of component k (K-gram, once per ensemble -- the counterpart of the reference's
+        precalculate()).  With it the fused kernel sweeps the columns x_<c once per evaluation instead of twice
+        (dJ/da = G a + mean_i M_i psi_i).  None when the two-sweep kernel is used (TTM_GRAM=0, no nonmonotone
+        terms, or nonmonotone polynomial order > 3).  Off by default: measured slower than two sweeps."""
+        if k in self._gram_nn:
+            return self._gram_nn[k]
+        with self._gram_lock:
+            if k not in self._gram_nn:
+                p = self._host_plans[k]
+                G = None
+                if self._use_gram and p.m_non > 0 and p.dense_maxord <= 3:
+                    G = np.ascontiguousarray(self._gram(k)[:p.m_non, :p.m_non]) / self._N_global
+                    B.check(self._lib.ttm_plan_set_gram_mode(self._plans[k], 1))
+                else:
+                    B.check(self._lib.ttm_plan_set_gram_mode(self._plans[k], 0))
+                self._gram_nn[k] = G
+        return self._gram_nn[k]
 
     def _reg_lambda(self, k, div):
         lam = self.regularization_lambda
