@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(T_INV) inverse_table_kernel(const InvArgs a) {
     double* s_pts = s_out + a.ntab;      // abscissae
     for (int j = threadIdx.x; j < m; j += T_INV) s_coef[j] = a.coeffs[j];
     for (int j = threadIdx.x; j < 2 * a.ntab; j += T_INV) s_out[j] = a.table[j];
+    const DenseSmem DS = stage_dense_tables(P, a.coeffs, m + 2 * a.ntab, threadIdx.x, T_INV);
     __syncthreads();
     const double tmin = s_out[0], tmax = s_out[a.ntab - 1];
     const int64_t rows = (a.N + T_INV - 1) / T_INV;
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(T_INV) inverse_table_kernel(const InvArgs a) {
             idx[r] = ok[r] ? i : a.N - 1;
             S[r] = 0.0;
         }
-        nonmon_sweep_rt<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);   // offset (:4039-4043)
+        dense_value_smem_rt<R_OBJ>(P, DS, a.Xt, a.ld, row0 * T_INV + threadIdx.x, T_INV, ok, S);   // offset (:4039-4043)
+        nonmon_slow_rt<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);
 #pragma unroll
         for (int r = 0; r < R_OBJ; ++r) {
             if (!ok[r]) continue;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(T_INV) inverse_bisect_kernel(const InvArgs a) 
         s_xis[q] = a.xis[q];
         s_ws[q] = a.ws[q];
     }
+    const DenseSmem DS = stage_dense_tables(P, a.coeffs, m + 2 * a.Q, threadIdx.x, T_INV);
     __syncthreads();
     const int64_t rows = (a.count + T_INV - 1) / T_INV;
     double* xc_col = a.Xt + (int64_t)P.c * a.ld;
@@ -153,7 +156,8 @@ __global__ void __launch_bounds__(T_INV) inverse_bisect_kernel(const InvArgs a) 
             idx[r] = ok[r] ? i : a.first;
             S[r] = 0.0;
         }
-        nonmon_sweep_rt<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);
+        dense_value_smem_rt<R_OBJ>(P, DS, a.Xt, a.ld, a.first + row0 * T_INV + threadIdx.x, T_INV, ok, S);
+        nonmon_slow_rt<false>(P, a.Xt, a.ld, idx, s_coef, S, nullptr, 0);
 #pragma unroll 1
         for (int r = 0; r < R_OBJ; ++r) {
             if (!ok[r]) continue;
@@ -224,7 +228,7 @@ cudaError_t ttm_launch_inverse_table(const InvArgs& a, cudaStream_t st) {
     const int64_t rows = (a.N + T_INV - 1) / T_INV;
     int64_t grid = (rows + R_OBJ - 1) / R_OBJ;
     if (grid > 148 * 16) grid = 148 * 16;
-    const size_t smem = sizeof(double) * (size_t)(a.P.m_non + a.P.m_mon + 2 * a.ntab);
+    const size_t smem = sizeof(double) * (size_t)(a.P.m_non + a.P.m_mon + 2 * a.ntab + dense_smem_doubles(a.P.ndense, a.P.dense_maxord));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(inverse_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -239,7 +243,7 @@ cudaError_t ttm_launch_inverse_bisect(const InvArgs& a, cudaStream_t st) {
     const int64_t rows = (a.count + T_INV - 1) / T_INV;
     int64_t grid = (rows + R_OBJ - 1) / R_OBJ;
     if (grid > 148 * 16) grid = 148 * 16;
-    const size_t smem = sizeof(double) * (size_t)(a.P.m_non + a.P.m_mon + 2 * a.Q);
+    const size_t smem = sizeof(double) * (size_t)(a.P.m_non + a.P.m_mon + 2 * a.Q + dense_smem_doubles(a.P.ndense, a.P.dense_maxord));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(inverse_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const
     extern __shared__ double s_coef[];
     const int m = P.m_non + P.m_mon;
     for (int j = threadIdx.x; j < m; j += T_SEP) s_coef[j] = coeffs[j];
+    const DenseSmem DS = stage_dense_tables(P, coeffs, m, threadIdx.x, T_SEP);
     __syncthreads();
     const double* acoef = s_coef;
     const double* bcoef = s_coef + P.m_non;
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const
             S[r] = 0.0;
         }
         if (S_out) {
-            nonmon_sweep_rt<false>(P, Xt, ld, idx, acoef, S, nullptr, 0);
+            dense_value_smem_rt<R_OBJ>(P, DS, Xt, ld, row0 * T_SEP + threadIdx.x, T_SEP, ok, S);
+            nonmon_slow_rt<false>(P, Xt, ld, idx, acoef, S, nullptr, 0);
             for (int j = 0; j < P.m_mon; ++j) {
                 const double b = bcoef[j];
 #pragma unroll
@@ -155,7 +157,7 @@ cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld,
     const int64_t rows = (N + T_SEP - 1) / T_SEP;
     int64_t grid = (rows + R_OBJ - 1) / R_OBJ;
     if (grid > 148 * 16) grid = 148 * 16;
-    const size_t smem = sizeof(double) * (size_t)(P.m_non + P.m_mon);
+    const size_t smem = sizeof(double) * (size_t)(P.m_non + P.m_mon + dense_smem_doubles(P.ndense, P.dense_maxord));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(sep_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
