@@ -217,6 +217,10 @@ def inverse_metric(rank, world, dist, torch):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    # native libraries (NCCL's version banner, ...) write to fd 1: keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', '0'))
@@ -420,7 +424,10 @@ def run_gpu(args):
                           'evals/s scaled linearly to N=1M; host has %d cores' % (n_cpu, os.environ.get('OPENBLAS_NUM_THREADS'), cores)}
         if inv is not None:
             line['inverse_map'] = inv
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
