@@ -143,7 +143,7 @@ static int parse_view(ttm_plan* p, const int32_t* h) {
     v.o_ent_i = h[H_ENT_I]; v.o_multi_idx = h[H_MULTI_IDX];
     v.o_slot_ptr = h[H_SLOT_PTR]; v.o_slot_term = h[H_SLOT_TERM];
     v.o_out_ptr = h[H_OUT_PTR]; v.o_out_fac = h[H_OUT_FAC]; v.o_st_fac = h[H_ST_FAC];
-    v.ndense = h[H_NDENSE]; v.dense_maxord = h[H_DENSE_MAXORD]; v.nactive = h[H_NACTIVE];
+    v.ndense = h[H_NDENSE]; v.dense_maxord = h[H_DENSE_MAXORD]; v.nactive = h[H_NACTIVE]; v.n_outfac = h[H_NOUTFAC];
     v.o_dense_var = h[H_DENSE_VAR]; v.o_dense_idx = h[H_DENSE_IDX]; v.o_d_dense_scale = h[H_D_DENSE_SCALE];
     v.o_d_fac = h[H_D_FAC]; v.o_d_ent = h[H_D_ENT]; v.o_d_slot_scale = h[H_D_SLOT_SCALE]; v.o_d_rec = h[H_D_REC];
     // alignment of the vector-loaded records

@@ -55,6 +55,7 @@ enum {
     // dense nonmonotone groups: per variable, polynomial coefficients addressed by slot 2*order+hf
     H_NDENSE, H_DENSE_VAR, H_DENSE_IDX, H_DENSE_MAXORD, H_D_DENSE_SCALE,
     H_NACTIVE,      // number of non-empty monotone slots
+    H_NOUTFAC,      // total number of outer-factor entries of the monotone terms
     H_SIZE = 48
 };
 
@@ -64,7 +65,7 @@ struct PlanView {
     int dtot, c, family, nfac;
     int m_non, m_mon, m_dmon;
     int nconst, nvars, nmulti;
-    int ndense, dense_maxord, nactive;
+    int ndense, dense_maxord, nactive, n_outfac;
     int maxord, has_plain, has_hf, nst, nslot;
     // offsets
     int o_fac_i, o_non_ptr, o_non_fac, o_mon_ptr, o_mon_fac, o_dmon_ptr, o_dmon_fac;

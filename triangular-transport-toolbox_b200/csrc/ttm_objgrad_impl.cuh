@@ -49,11 +49,12 @@ __device__ __forceinline__ void ladder(double t, const double* __restrict__ rec,
 }
 
 // outer (x_<c) product of monotone term j on sample i; 1 if the term has no outer factor
-static __device__ __noinline__ double outer_product(const PlanView& P, int j, const double* __restrict__ Xt,
-                                                    int64_t ld, int64_t i) {
-    const int b = __ldg(P.ib + P.o_out_ptr + j), e = __ldg(P.ib + P.o_out_ptr + j + 1);
+static __device__ __noinline__ double outer_product(const PlanView& P, const int* __restrict__ out_ptr,
+                                                    const int* __restrict__ out_fac, int j,
+                                                    const double* __restrict__ Xt, int64_t ld, int64_t i) {
+    const int b = out_ptr[j], e = out_ptr[j + 1];
     double v = 1.0;
-    for (int q = b; q < e; ++q) v *= plan_factor(P, __ldg(P.ib + P.o_out_fac + q), Xt, ld, i);
+    for (int q = b; q < e; ++q) v *= plan_factor(P, out_fac[q], Xt, ld, i);
     return v;
 }
 
@@ -83,7 +84,12 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     double* s_dscale = s_dprod + ndt;
     int4* s_dvar = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(s_dscale + ndt) + 15) & ~uintptr_t(15));
     int* s_didx = reinterpret_cast<int*>(s_dvar + P.ndense);
-    double* s_S = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_didx + ndt) + 15) & ~uintptr_t(15));  // [CH_ROWS][T_OBJ]
+    // monotone slot tables (the per-row-group prologue/epilogue walks them; from L2 they cost ~300 cycles per hop)
+    int* s_slot_ptr = s_didx + ndt;                      // [nslot_rt + 1]
+    int* s_slot_term = s_slot_ptr + nslot_rt + 1;        // [m_mon]
+    int* s_out_ptr = s_slot_term + P.m_mon;              // [m_mon + 1]
+    int* s_out_fac = s_out_ptr + P.m_mon + 1;            // [n_outfac]
+    double* s_S = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_out_fac + P.n_outfac) + 15) & ~uintptr_t(15));  // [ch_rows][T_OBJ]
 
     for (int j = tid; j < m; j += T_OBJ) s_coef[j] = a.coeffs[j];
     for (int q = tid; q < Qp; q += T_OBJ) {              // padding nodes: mid-point, zero weight
@@ -106,6 +112,10 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
         s_dprod[e] = (j >= 0) ? a.coeffs[j] * sc : 0.0;
     }
     for (int g = tid; g < P.ndense; g += T_OBJ) s_dvar[g] = reinterpret_cast<const int4*>(P.ib + P.o_dense_var)[g];
+    for (int e = tid; e <= nslot_rt; e += T_OBJ) s_slot_ptr[e] = P.ib[P.o_slot_ptr + e];
+    for (int e = tid; e < P.m_mon; e += T_OBJ) s_slot_term[e] = P.ib[P.o_slot_term + e];
+    for (int e = tid; e <= P.m_mon; e += T_OBJ) s_out_ptr[e] = P.ib[P.o_out_ptr + e];
+    for (int e = tid; e < P.n_outfac; e += T_OBJ) s_out_fac[e] = P.ib[P.o_out_fac + e];
     __syncthreads();
     DenseTabs DT;
     DT.var = s_dvar; DT.idx = s_didx; DT.scale = s_dscale; DT.coefprod = s_dprod;
@@ -213,19 +223,19 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
             // slot coefficients C_s = scale_s * sum_{j in s} b_j u_j   (rolled over the plan's slots)
 #pragma unroll 1
             for (int s = 0; s < nslot_rt; ++s) {
-                const int j0 = __ldg(P.ib + P.o_slot_ptr + s), j1 = __ldg(P.ib + P.o_slot_ptr + s + 1);
+                const int j0 = s_slot_ptr[s], j1 = s_slot_ptr[s + 1];
                 if (j0 == j1) continue;
                 const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
                 double acc[RB];
 #pragma unroll
                 for (int rb = 0; rb < RB; ++rb) acc[rb] = 0.0;
                 for (int jj = j0; jj < j1; ++jj) {
-                    const int j = __ldg(P.ib + P.o_slot_term + jj);
+                    const int j = s_slot_term[jj];
                     const double b = bcoef[j];
-                    const bool has_outer = __ldg(P.ib + P.o_out_ptr + j) != __ldg(P.ib + P.o_out_ptr + j + 1);
+                    const bool has_outer = s_out_ptr[j] != s_out_ptr[j + 1];
 #pragma unroll
                     for (int rb = 0; rb < RB; ++rb)
-                        acc[rb] = fma(b, has_outer ? outer_product(P, j, Xt, ld, idx[r0 + rb]) : 1.0, acc[rb]);
+                        acc[rb] = fma(b, has_outer ? outer_product(P, s_out_ptr, s_out_fac, j, Xt, ld, idx[r0 + rb]) : 1.0, acc[rb]);
                 }
                 const double sc = s_scale[s];
 #pragma unroll
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 int ai = 0;
 #pragma unroll 1
                 for (int s = 0; s < nslot_rt; ++s) {
-                    if (__ldg(P.ib + P.o_slot_ptr + s) == __ldg(P.ib + P.o_slot_ptr + s + 1)) continue;
+                    if (s_slot_ptr[s] == s_slot_ptr[s + 1]) continue;
                     const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
 #pragma unroll
                     for (int rb = 0; rb < RB; ++rb)
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 int ai = 0;
 #pragma unroll 1
                 for (int s = 0; s < nslot_rt; ++s) {
-                    if (__ldg(P.ib + P.o_slot_ptr + s) == __ldg(P.ib + P.o_slot_ptr + s + 1)) continue;
+                    if (s_slot_ptr[s] == s_slot_ptr[s + 1]) continue;
                     const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
 #pragma unroll
                     for (int rb = 0; rb < RB; ++rb)
@@ -442,7 +452,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                 // dJ/db_j = sum_i u_ij [ S_i hx_i I_{i,s} - ratio_i phi_s(x_ic) ],  s = slot of term j
 #pragma unroll 1
                 for (int s = 0; s < nslot_rt; ++s) {
-                    const int j0 = __ldg(P.ib + P.o_slot_ptr + s), j1 = __ldg(P.ib + P.o_slot_ptr + s + 1);
+                    const int j0 = s_slot_ptr[s], j1 = s_slot_ptr[s + 1];
                     if (j0 == j1) continue;
                     const int ts = (s < st_base) ? s : 2 * (MAXORD + 1) + (s - st_base);
                     const double sc = s_scale[s];
@@ -451,12 +461,12 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                     for (int rb = 0; rb < RB; ++rb)
                         W[rb] = valid[r0 + rb] * sc * (Sfull[rb] * hx[rb] * tmp[rb][ts] - ratio[rb] * base[rb][ts]);
                     for (int jj = j0; jj < j1; ++jj) {
-                        const int j = __ldg(P.ib + P.o_slot_term + jj);
-                        const bool has_outer = __ldg(P.ib + P.o_out_ptr + j) != __ldg(P.ib + P.o_out_ptr + j + 1);
+                        const int j = s_slot_term[jj];
+                        const bool has_outer = s_out_ptr[j] != s_out_ptr[j + 1];
                         double v = 0.0;
 #pragma unroll
                         for (int rb = 0; rb < RB; ++rb)
-                            v = fma(has_outer ? outer_product(P, j, Xt, ld, idx[r0 + rb]) : 1.0, W[rb], v);
+                            v = fma(has_outer ? outer_product(P, s_out_ptr, s_out_fac, j, Xt, ld, idx[r0 + rb]) : 1.0, W[rb], v);
                         v = warp_sum(v);
                         if (lane == 0) gslot[P.m_non + j] += v;
                     }

@@ -30,7 +30,7 @@ PLAN_MAGIC = 0x54544d31
  H_NCONST, H_CONST_IDX, H_NVARS, H_VAR_IDX, H_VAR_PTR, H_ENT_I, H_NMULTI, H_MULTI_IDX,
  H_MAXORD, H_HAS_PLAIN, H_HAS_HF, H_NST, H_NSLOT, H_SLOT_PTR, H_SLOT_TERM, H_OUT_PTR, H_OUT_FAC, H_ST_FAC,
  H_D_FAC, H_D_ENT, H_D_SLOT_SCALE, H_D_REC, H_NON_MAXVAR,
- H_NDENSE, H_DENSE_VAR, H_DENSE_IDX, H_DENSE_MAXORD, H_D_DENSE_SCALE, H_NACTIVE) = range(44)
+ H_NDENSE, H_DENSE_VAR, H_DENSE_IDX, H_DENSE_MAXORD, H_D_DENSE_SCALE, H_NACTIVE, H_NOUTFAC) = range(45)
 H_SIZE = 48
 
 _ST_KIND = {'rbf': F_RBF, 'irbf': F_IRBF, 'let': F_LET, 'ret': F_RET}
@@ -345,6 +345,7 @@ class ComponentPlan:
         h[H_NON_MAXVAR] = non_maxvar
         h[H_NDENSE], h[H_DENSE_MAXORD] = len(dense_var), dense_maxord
         h[H_NACTIVE] = sum(1 for t in slot_terms if len(t))
+        h[H_NOUTFAC] = sum(len(t) for t in outer)
         h[H_DENSE_VAR] = put_i(dense_var, 4)
         h[H_DENSE_IDX] = put_i(np.concatenate(dense_idx) if dense_idx else [])
         h[H_D_DENSE_SCALE] = put_d(np.concatenate(dense_scale) if dense_scale else [])
