@@ -110,6 +110,8 @@ class transport_map():
         self._sharded = bool(sample_sharded) and self._world > 1
         import os as _os
         self.fit_threads = int(fit_threads if fit_threads is not None else _os.environ.get('TTM_FIT_THREADS', 2))
+        if fit_threads is None and isinstance(workers, int) and workers > 1:
+            self.fit_threads = min(int(workers), 4)     # the reference's process pool becomes host threads + streams
         self._use_gram = _os.environ.get('TTM_GRAM', '0') != '0'   # experimental one-sweep kernel, see DESIGN.md
         import threading as _threading
         self._gram_lock = _threading.Lock()
