@@ -58,7 +58,7 @@ torch.cuda.synchronize()
 tmap = time.perf_counter() - t
 if rank == 0:
     print(json.dumps({'n': n, 'D': D, 'Q': q, 'gpus': world, 'ctor_s': ctor, 'optimize_s': fit,
-                      'fused_evals_this_rank': calls['n'], 'max_abs_grad_at_solution': gmax,
+                      'fused_evals_this_rank': calls['n'], 'timing_rank0': tm._last_timing, 'max_abs_grad_at_solution': gmax,
                       'sum_J': float(np.sum(Js)), 'map_200k_s': tmap,
                       'Z_mean_abs_max': float(np.max(np.abs(Z.mean(axis=0)))), 'Z_std_range': [float(Z.std(axis=0).min()), float(Z.std(axis=0).max())]}))
 if world > 1:

@@ -108,6 +108,10 @@ class transport_map():
         from .parallel import world
         self._rank, self._world = world()
         self._sharded = bool(sample_sharded) and self._world > 1
+        if self._world > 1:
+            # create the communicator now (the first NCCL collective costs ~3 s) instead of inside optimize()
+            from .parallel import allreduce_sum
+            allreduce_sum(np.zeros(1), self._device)
         import os as _os
         self.fit_threads = int(fit_threads if fit_threads is not None else _os.environ.get('TTM_FIT_THREADS', 2))
         if fit_threads is None and isinstance(workers, int) and workers > 1:
@@ -706,6 +710,8 @@ class transport_map():
             rank, size = 0, 1                  # every rank fits every component on its shard, in lockstep
         mine = shard_components(K, rank, size)
         results = {}
+        import time as _time
+        _t0 = _time.perf_counter()
         nthreads = self.fit_threads if (self.monotonicity == "integrated rectifier" and not self._sharded) else 1
         if nthreads > 1 and len(mine) > 1:
             # components are independent: a few host threads, each on its own stream with a reduced grid per
@@ -733,9 +739,11 @@ class transport_map():
                 results[k] = fit(k, None)
                 if self.verbose and size == 1:
                     print('\r' + 'Progress: |' + (K.index(k) + 1) * '█' + (len(K) - K.index(k) - 1) * ' ' + '|', end='\r')
+        _t1 = _time.perf_counter()
         if size > 1:
             results = allgather_coeffs(results, K, [self._host_plans[k].m_non for k in K],
                                        [self._host_plans[k].m_mon for k in K], self._device)
+        self._last_timing = {'fit_s': _t1 - _t0, 'gather_s': _time.perf_counter() - _t1, 'components': len(mine)}
         for k in K:
             self.coeffs_nonmon[k] = copy.deepcopy(results[k][0])
             self.coeffs_mon[k] = copy.deepcopy(results[k][1])
