@@ -250,7 +250,6 @@ static int fill_obj(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, ObjArg
     if (!Xt || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "bad sample matrix");
     a.P = p->view;
     a.Xt = Xt; a.ld = ld; a.N = N;
-    if (getenv("TTM_DEBUG_LD0")) a.ld = 0;  // experiment: alias every column to column 0 (L2-resident)
     a.coeffs = p->d_coeffs;
     a.xis = c->d_xis; a.ws = c->d_ws; a.Q = c->Q; a.wsum = c->wsum;
     a.rect = c->rect; a.delta = c->delta;

@@ -76,3 +76,18 @@ def allreduce_sum(vec, device=None):
     t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
+
+
+def warm_up(device=None):
+    """Create the communicator and the all-reduce / all-gather channels now: the first NCCL collective of each
+    kind costs seconds, which would otherwise be charged to the first optimize()."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend()
+    dev = device if (backend == 'nccl' and device is not None) else torch.device('cpu')
+    t = torch.zeros(8, dtype=torch.float64, device=dev)
+    dist.all_reduce(t)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    if dev.type == 'cuda':
+        torch.cuda.synchronize(dev)

@@ -110,8 +110,8 @@ class transport_map():
         self._sharded = bool(sample_sharded) and self._world > 1
         if self._world > 1:
             # create the communicator now (the first NCCL collective costs ~3 s) instead of inside optimize()
-            from .parallel import allreduce_sum
-            allreduce_sum(np.zeros(1), self._device)
+            from .parallel import warm_up
+            warm_up(self._device)
         import os as _os
         self.fit_threads = int(fit_threads if fit_threads is not None else _os.environ.get('TTM_FIT_THREADS', 2))
         if fit_threads is None and isinstance(workers, int) and workers > 1:
