@@ -168,7 +168,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # secondary metric M2: conditional sampling via inverse_map (config C5)
 # ------------------------------------------------------------------------------------------------
-def inverse_metric(rank, world, dist, torch):
+def inverse_metric(rank, world, dist, torch, with_cpu=False):
     """C5: D=256 separable map (LET/iRBF/iRBF/RET + order-3 nonmonotone terms), trained on 10^4
     samples (components sharded over the ranks, one all-gather), then inverse_map(Z, X_star) with E=128
     conditioning columns on 1.25M samples PER GPU (10M over 8 GPUs), through the public class API with host
@@ -205,12 +205,43 @@ def inverse_metric(rank, world, dist, torch):
         if not alt:
             resid = float(np.max(np.abs(tm.map(Xs[:20000])[:, E:] - Z[:20000])))
             res[mode]['max_residual'] = resid
-    return {'metric': 'inverse_map samples/sec', 'value': res['table']['samples_per_s'], 'unit': 'samples/s',
+    cpu = None
+    if with_cpu and rank == 0 and world == 1:
+        cpu = inverse_cpu_port(tm, mon, non, Dm, E)
+    out = {'metric': 'inverse_map samples/sec', 'value': res['table']['samples_per_s'], 'unit': 'samples/s',
             'config': {'workload': 'C5: D=256 separable map, conditional sampling with E=128, %d samples per GPU, '
                                    'default table root finder (alternate_root_finding=True); steady state (second full-size call)' % ns,
                        'n_train': ntrain},
             'bisection': res['bisection'], 'table': res['table'], 'ctor_s': ctor_s, 'optimize_s': opt_s,
             'scaling': 'weak', 'e2e': True}
+    if cpu is not None:
+        out['cpu_baseline'] = cpu
+    return out
+
+
+def inverse_cpu_port(tm, mon, non, Dm, E, ntrain=2000, n_table=2000):
+    """CPU leg of M2: the oracle's inverse_map (tm.py:3639-4084 restated) of the same C5 map on a bounded sample.
+    The oracle materialises every Psi of the training set like the reference (7.8 GB at 10^4 samples), so it is
+    built on the first `ntrain` training samples and given the coefficients fitted on the GPU; its cost per
+    conditional sample does not depend on the training set."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from ttm_oracle import OracleMap
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', str(os.cpu_count()))
+    om = OracleMap(X=synthetic_samples(ntrain, Dm, seed=0), monotone=mon, nonmonotone=non,
+                   monotonicity='separable monotonicity')
+    for k in range(Dm):
+        om.coeffs_nonmon[k] = np.array(tm.coeffs_nonmon[k], dtype=np.float64)
+        om.coeffs_mon[k] = np.array(tm.coeffs_mon[k], dtype=np.float64)
+    rng = np.random.default_rng(300)
+    Xstar = synthetic_samples(n_table, Dm, seed=301)[:, :E].copy()
+    Z = rng.standard_normal((n_table, Dm - E))
+    om.alternate_root_finding = True         # the default root finder (the oracle's bisection arm has ~60 s of fixed
+    t = time.perf_counter()                  # cost per call at D=256 and is left to the parity tests)
+    om.inverse_map(Z, X_star=Xstar)
+    v = n_table / (time.perf_counter() - t)
+    return {'value': v, 'unit': 'samples/s', 'cores': 1, 'kind': 'port',
+            'sample': 'oracle inverse_map of the same C5 map (coefficients from the GPU fit, oracle built on %d training '
+                      'samples): %d conditional samples, table root finder, single process' % (ntrain, n_table)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -360,7 +391,7 @@ def run_gpu(args):
     if not args.no_inverse:
         del tm, flush
         torch.cuda.empty_cache()
-        inv = inverse_metric(rank, world, dist, torch)
+        inv = inverse_metric(rank, world, dist, torch, with_cpu=not args.no_cpu)
 
     if rank == 0:
         value = D * args.steps / t_max
@@ -381,9 +412,14 @@ def run_gpu(args):
         achieved = fl / t_kernels / 1e12
         roofline = {
             'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
-            'traffic': None,
-            'traffic_ncu': {'k63_bytes': 1.05e9, 'k0_bytes': 2.1e7, 'algorithmic_k63_bytes': 5.12e8,
-                            'source': 'profiles/ncu_objgrad_k63_r1.txt, ncu_objgrad_k0_r1.txt (dram read+write per launch, N=1M)'},
+            # dram__bytes_read.sum + dram__bytes_write.sum of the 64 launches of one step (N=1M, 1 GPU), per launch:
+            # 32.87 GB read + 2.97 GB written / 64.  Algorithmic: 8 N (k+1), 260 MB on average -- the kernel sweeps
+            # the columns x_<c twice (value, gradient); the writes are the spilled node-loop state.
+            'traffic': 5.60e8 if (n == N_FULL and world == 1) else None,
+            'traffic_ncu': {'per_launch_avg_bytes': 5.60e8, 'k63_bytes': 1.10e9, 'k0_bytes': 2.4e7,
+                            'algorithmic_per_launch_avg_bytes': 2.60e8,
+                            'source': 'profiles/ncu_traffic_64launches_r1.csv (ncu --metrics dram__bytes_read.sum,'
+                                      'dram__bytes_write.sum over the 64 launches of one bench step, N=1M)'},
             'peak_source': 'ttm_fp64_peak: dependent-free DFMA chains, measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
             'flops_per_launch_avg': fl / len(mine), 'bytes_per_launch_avg': by / len(mine),
             'launch_ms_avg': t_kernels / len(mine) * 1e3,
