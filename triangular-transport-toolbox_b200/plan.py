@@ -92,10 +92,15 @@ def parse_entry(entry, st_counter, c, monotone_fn, linearization):
     if lin and linearization is None:
         raise Exception("'LIN' modifier specified in variable monotone, but the variable linearization is "
                         "defined as None. Please specify a scalar linearization or remove the 'LIN' modifier.")
-    ints = [e for e in entry if type(e) != str]
-    ui, ct = np.unique(ints, return_counts=True)
+    # sorted distinct variables and their multiplicities (np.unique(..., return_counts=True) of tm.py:1430,
+    # written out: the lists have a handful of entries and this runs once per term)
+    counts = {}
+    for e in entry:
+        if type(e) != str:
+            counts[int(e)] = counts.get(int(e), 0) + 1
+    ui = sorted(counts)
     # NB 'LIN' is a numerical no-op in the reference: the factor is evaluated as is.
-    return {'type': 'poly', 'hf': hf, 'vars': [int(u) for u in ui], 'orders': [int(n) for n in ct]}
+    return {'type': 'poly', 'hf': hf, 'vars': ui, 'orders': [counts[u] for u in ui]}
 
 
 class _Factors:

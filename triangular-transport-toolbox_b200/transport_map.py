@@ -200,7 +200,7 @@ class transport_map():
             self.optimization_constraints_lb = [p.lb.copy() for p in self._host_plans]
             self.optimization_constraints_ub = [p.ub.copy() for p in self._host_plans]
         self._make_callables()
-        self.precalculate()
+        self._reset_lazy()          # precalculate() without re-placing the special terms a second time
 
     # ================================================================== plumbing
     def _stream(self):
@@ -447,6 +447,9 @@ class transport_map():
         access (the fused kernels never read them)."""
         self.determine_special_term_locations()
         self._refresh_special_terms()
+        self._reset_lazy()
+
+    def _reset_lazy(self):
         self.Psi_nonmon = _LazyList(self.D, lambda k: self._basis(k, 0, self._Xt, self._N))
         self.Psi_mon = _LazyList(self.D, lambda k: self._basis(k, 1, self._Xt, self._N))
         if self.monotonicity.lower() == 'separable monotonicity':
@@ -649,11 +652,12 @@ class transport_map():
         N = self._N_global
         if self.regularization is None:
             # scaled Cholesky solve (Jacobi preconditioning tames the squared condition number)
+            from scipy.linalg import cholesky, solve_triangular
             d = 1.0 / np.sqrt(np.maximum(np.diag(Gnn), np.finfo(float).tiny))
-            L = np.linalg.cholesky(Gnn * d[:, None] * d[None, :])
-            Y = np.linalg.solve(L, Gnm * d[:, None])
+            L = cholesky(Gnn * d[:, None] * d[None, :], lower=True, overwrite_a=True, check_finite=False)
+            Y = solve_triangular(L, Gnm * d[:, None], lower=True, check_finite=False)
             A = (Gmm - Y.T @ Y) / N
-            back = lambda b: -(d * np.linalg.solve(L.T, Y @ b))
+            back = lambda b: -(d * solve_triangular(L, Y @ b, lower=True, trans='T', check_finite=False))
         elif self.regularization.lower() == 'l2':
             lam = self.regularization_lambda
             Bm = np.linalg.solve(Gnn + lam * np.identity(mn), Gnm)
