@@ -157,3 +157,39 @@ def test_gram_mode_equals_two_sweep_kernel_and_oracle():
             assert tg._gram_nn[k] is not None and t2._gram_nn[k] is None
             assert abs(Jg - Jo) <= 1e-10 * max(1, abs(Jo)) and abs(J2 - Jo) <= 1e-10 * max(1, abs(Jo))
             assert rel_err(gg, go) <= 1e-10 and rel_err(g2, go) <= 1e-10
+
+
+@pytest.mark.parametrize('conditioning', ['x_star', 'skip_dimensions', 'skip_dimensions_unconditioned', 'none'])
+def test_pipelined_inverse_is_bit_identical_to_one_shot(conditioning, monkeypatch):
+    """Large table-mode inverse_map calls are cut into chunks of samples that overlap staging, copies and
+    solves (transport_map._inverse_map_pipelined); samples are independent, so the chunked result must equal
+    the one-shot result bit for bit -- including a ragged last chunk and a slot that is reused."""
+    from cases import ex06_terms
+    n_train, n = 600, 2503
+    if conditioning.startswith('skip_dimensions'):
+        mon, non = ex06_terms(3)
+        X = synthetic_samples(n_train, 4, seed=3)
+        tm = make_cuda(X, monotone=mon, nonmonotone=non, monotonicity='separable monotonicity',
+                       regularization='l2', regularization_lambda=0.05)
+        tm.optimize()
+        rng = np.random.default_rng(5)
+        Z, Xs = rng.standard_normal((n, 3)), synthetic_samples(n, 4, seed=9)[:, :1].copy()
+        if conditioning.endswith('unconditioned'):
+            Xs = None
+    else:
+        mon, non = ex05_terms()
+        X = synthetic_samples(n_train, 2, seed=4)
+        tm = make_cuda(X, monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+        tm.optimize()
+        rng = np.random.default_rng(6)
+        if conditioning == 'x_star':
+            Z, Xs = rng.standard_normal((n, 1)), synthetic_samples(n, 2, seed=8)[:, :1].copy()
+        else:
+            Z, Xs = rng.standard_normal((n, 2)), None
+    monkeypatch.setenv('TTM_INV_PIPELINE_MIN', '1000000000')
+    one_shot = tm.inverse_map(Z, X_star=Xs)
+    monkeypatch.setenv('TTM_INV_PIPELINE_MIN', '1000')
+    monkeypatch.setenv('TTM_INV_CHUNK', '600')          # 5 chunks of 501 through 3 slots, the last one ragged (499)
+    piped = tm.inverse_map(Z, X_star=Xs)
+    assert piped.shape == one_shot.shape
+    assert np.array_equal(piped, one_shot)

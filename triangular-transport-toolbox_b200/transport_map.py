@@ -16,6 +16,7 @@ PyTorch is used for device buffers, streams and (multi-GPU) torch.distributed on
 """
 
 import copy
+import os
 
 import numpy as np
 
@@ -772,6 +773,9 @@ class transport_map():
         if ncol != self._Dtot:
             raise ValueError("operands could not be broadcast together: %d columns vs %d" % (ncol, self._Dtot))
         torch = self._torch
+        table_mode = self.alternate_root_finding and self.monotonicity.lower() == 'separable monotonicity'
+        if table_mode and N >= int(os.environ.get('TTM_INV_PIPELINE_MIN', 131072)):
+            return self._inverse_map_pipelined(Z, X_star, E, ncol, comps)
         Xw = torch.zeros(ncol, N, dtype=torch.float64, device=self._device)
         if E > 0:
             std = self.standardize_samples
@@ -779,7 +783,6 @@ class transport_map():
                                    self._std_d[:E].contiguous() if std else None)
             Xw[:E] = Xs
         Zt = self._to_colmajor(Z)
-        table_mode = self.alternate_root_finding and self.monotonicity.lower() == 'separable monotonicity'
         for i, k in comps:
             self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
             if table_mode:
@@ -793,19 +796,108 @@ class transport_map():
             Xout = self._to_rowmajor(Xw[skip:], N, ncol - skip)
         return Xout
 
-    def _root_search_table(self, k, Xw, N, z, start_distance=10, resolution=1001):
-        """vectorized_root_search_alternate (tm.py:3987-4084): table on the device, argsort on the host
-        (scipy interp1d sorts its abscissae), interpolation per sample on the device."""
+    def _monotone_table(self, k, start_distance=10, resolution=1001):
+        """The lookup table of vectorized_root_search_alternate (tm.py:4047-4062) for component k (coefficients
+        already set): monotone part on a grid, evaluated on the device, sorted on the host like scipy's interp1d.
+        It depends on the coefficients only, not on the samples."""
         pts = np.linspace(-start_distance, start_distance, resolution)
         tab = self._empty(2 * resolution)
         tab[resolution:] = self._upload(pts)
         B.check(self._lib.ttm_mon_table(self._plans[k], resolution, B.c_void_p(tab.data_ptr()), self._stream()))
         out = tab[:resolution].cpu().numpy()
         ind = np.argsort(out, kind="mergesort")
-        tab = self._upload(np.concatenate((out[ind], pts[ind])))
+        return self._upload(np.concatenate((out[ind], pts[ind])))
+
+    def _root_search_table(self, k, Xw, N, z, start_distance=10, resolution=1001):
+        """vectorized_root_search_alternate (tm.py:3987-4084): table on the device, argsort on the host
+        (scipy interp1d sorts its abscissae), interpolation per sample on the device."""
+        tab = self._monotone_table(k, start_distance, resolution)
         B.check(self._lib.ttm_inverse_table(self._plans[k], B.c_void_p(Xw.data_ptr()), Xw.shape[1], N,
                                             B.c_void_p(z.data_ptr()), B.c_void_p(tab.data_ptr()), resolution,
                                             1 if self.root_search_truncation else 0, self._stream()))
+
+    def _inverse_map_pipelined(self, Z, X_star, E, ncol, comps, resolution=1001):
+        """Table-mode inverse_map for large sample counts.  Samples are independent (tm.py:3684-3698 loops over the
+        components, never across samples), so the call is cut into chunks of samples that flow through three
+        slots: host threads stage chunk c+1 into pinned memory while chunk c is copied, transposed, solved (one
+        K-inv-table launch per component) and chunk c-1 is copied back.  Bit-identical to the one-shot path."""
+        from concurrent.futures import ThreadPoolExecutor
+        torch, lib, dev = self._torch, self._lib, self._device
+        N, nz, skip = Z.shape[0], Z.shape[1], self.skip_dimensions
+        nout = ncol - skip
+        std = self.standardize_samples
+        tabs = []
+        for _, k in comps:                                   # tables first: they need a host round trip each
+            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+            tabs.append(self._monotone_table(k, resolution=resolution))
+        mean_in = self._mean_d[:E].contiguous() if (std and E > 0) else None
+        std_in = self._std_d[:E].contiguous() if (std and E > 0) else None
+        mean_out = self._mean_d[skip:].contiguous() if std else None
+        std_out = self._std_d[skip:].contiguous() if std else None
+        torch.cuda.current_stream(dev).synchronize()
+        nchunk = max(2, -(-N // int(os.environ.get('TTM_INV_CHUNK', 163840))))
+        cap = -(-N // nchunk)
+        nslot = min(3, nchunk)
+        f64 = torch.float64
+        slots = []
+        for _ in range(nslot):
+            slots.append({
+                'stream': torch.cuda.Stream(device=dev), 'event': None,
+                'hz': torch.empty((cap, nz), dtype=f64, pin_memory=True),
+                'hx': torch.empty((cap, E), dtype=f64, pin_memory=True) if E > 0 else None,
+                'dz': torch.empty((cap, nz), dtype=f64, device=dev),
+                'dx': torch.empty((cap, E), dtype=f64, device=dev) if E > 0 else None,
+                'Xw': torch.empty((ncol, cap), dtype=f64, device=dev),
+                'Zt': torch.empty((nz, cap), dtype=f64, device=dev),
+                'out': torch.empty((cap, nout), dtype=f64, device=dev)})
+        out_host = torch.empty((N, nout), dtype=f64, pin_memory=True)
+        trunc = 1 if self.root_search_truncation else 0
+        ptr = lambda t: B.c_void_p(t.data_ptr()) if t is not None else None
+        nthr = 4
+
+        def stage(dst, src, n):                              # pageable -> pinned, split over host threads
+            edges = [n * t // nthr for t in range(nthr + 1)]
+            return [pool.submit(np.copyto, dst[edges[t]:edges[t + 1]], src[edges[t]:edges[t + 1]])
+                    for t in range(nthr) if edges[t + 1] > edges[t]]
+
+        with ThreadPoolExecutor(nthr) as pool:
+            for c in range(nchunk):
+                c0, c1 = c * cap, min(N, (c + 1) * cap)
+                n = c1 - c0
+                if n <= 0:
+                    break
+                sl = slots[c % nslot]
+                if sl['event'] is not None:
+                    sl['event'].synchronize()                # the slot's previous chunk is back on the host
+                futs = stage(sl['hz'].numpy(), Z[c0:c1], n)
+                if E > 0:
+                    futs += stage(sl['hx'].numpy(), X_star[c0:c1], n)
+                for f in futs:
+                    f.result()
+                with torch.cuda.stream(sl['stream']):
+                    st = self._stream()
+                    sl['dz'][:n].copy_(sl['hz'][:n], non_blocking=True)
+                    B.check(lib.ttm_standardize_transpose(self._ctx, ptr(sl['dz']), n, nz, None, None,
+                                                          ptr(sl['Zt']), cap, st))
+                    if E < skip:                             # unconditioned leading columns read as zero
+                        sl['Xw'][E:skip].zero_()
+                    if E > 0:
+                        sl['dx'][:n].copy_(sl['hx'][:n], non_blocking=True)
+                        B.check(lib.ttm_standardize_transpose(self._ctx, ptr(sl['dx']), n, E, ptr(mean_in), ptr(std_in),
+                                                              ptr(sl['Xw']), cap, st))
+                    for (i, k), tab in zip(comps, tabs):
+                        B.check(lib.ttm_inverse_table(self._plans[k], ptr(sl['Xw']), cap, n,
+                                                      B.c_void_p(sl['Zt'].data_ptr() + i * cap * 8), ptr(tab),
+                                                      resolution, trunc, st))
+                    B.check(lib.ttm_transpose_back(self._ctx, B.c_void_p(sl['Xw'].data_ptr() + skip * cap * 8), cap, n,
+                                                   nout, ptr(mean_out), ptr(std_out), ptr(sl['out']), nout, st))
+                    out_host[c0:c1].copy_(sl['out'][:n], non_blocking=True)
+                    sl['event'] = torch.cuda.Event()
+                    sl['event'].record()
+        for sl in slots:
+            if sl['event'] is not None:
+                sl['event'].synchronize()
+        return out_host.numpy()
 
     def _root_search_bisection(self, k, Xw, N, z, max_iterations=100):
         """vectorized_root_search_bisection (tm.py:3798-3985), one thread per sample."""
