@@ -19,7 +19,7 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a_in, bool grad, int sm_count, cud
     const int64_t rows = (a.N + T_OBJ - 1) / T_OBJ;
     const int nslot_rt = 2 * (P.maxord + 1) + P.nst;
     auto smem_for = [&](int maxord_t) {
-        return sizeof(double) * (size_t)(m + 2 * (a.Q + 4) + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0) +
+        return sizeof(double) * (size_t)(m + 2 * (a.Q + 4) + 32 + 3 * (maxord_t + 1) + nslot_rt + (grad ? (T_OBJ / 32) * (1 + m) : 0) +
                                         (size_t)P.ndense * 2 * (P.dense_maxord + 1) * 2 + 2 * P.ndense + 6) +
                sizeof(int) * (size_t)(P.ndense * 2 * (P.dense_maxord + 1) + 8 + nslot_rt + 2 * P.m_mon + P.n_outfac + 6) +
                sizeof(double) * ((size_t)a.ch_rows * T_OBJ * (1 + (a.gram_mode ? 1 + P.nactive : 0)) + 2);

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
     const int Qp = (a.Q + NQ - 1) / NQ * NQ;            // node count padded to a multiple of NQ
     double* s_xis = s_coef + m;
     double* s_ws = s_xis + Qp;
-    double* s_rec = s_ws + Qp;
+    double* s_exptab = s_ws + Qp;                        // 2^(j/32), j < 32: the exp table of the node loop
+    double* s_rec = s_exptab + 32;
     double* s_scale = s_rec + 3 * (MAXORD + 1);
     double* s_gacc = s_scale + nslot_rt;
     // dense nonmonotone tables staged after the gradient slots: coefficient products, scales, indices, groups
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
         s_xis[q] = (q < a.Q) ? a.xis[q] : 0.0;
         s_ws[q] = (q < a.Q) ? a.ws[q] : 0.0;
     }
+    for (int j = tid; j < 32; j += T_OBJ) s_exptab[j] = g_ttm_exp2_tab[j];
     for (int n = tid; n < 3 * (MAXORD + 1); n += T_OBJ) {
         double A, B, C;
         rec_coef(P.family, n % (MAXORD + 1), A, B, C);
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                         double y[L];
 #pragma unroll
                         for (int l = 0; l < L; ++l) y[l] = -0.25 * t[l] * t[l];
-                        ttm_exp_neg_v<L>(y, ga);
+                        ttm_exp_neg_v<L, true>(y, ga, s_exptab);
 #pragma unroll
                         for (int l = 0; l < L; ++l) r[l] = Ch[1][l % RB] * Pl[l][1];
 #pragma unroll
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
                         }
                     }
                     if (EXPRECT) {
-                        ttm_exp_v<L>(r, g);
+                        ttm_exp_v<L, true>(r, g, s_exptab);
                     } else {
 #pragma unroll
                         for (int l = 0; l < L; ++l) g[l] = rect_eval(a.rect, r[l]);
