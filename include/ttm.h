@@ -58,12 +58,20 @@ int ttm_ctx_set_rectifier(ttm_ctx* ctx, int rect, double delta);
  * (two components fitted by two host threads) share every SM and their phases overlap (+16 % throughput). */
 int ttm_ctx_set_blocks_per_sm(ttm_ctx* ctx, int blocks_per_sm);
 
+/* K-objgrad kernel selection: 0 (default) = the tile kernel (csrc/ttm_objgrad_tile.cu) whenever the component is in
+ * its class (order <= 3 Hermite functions, exponential rectifier; ttm_plan_info), 1 = always the general kernel.
+ * Both compute the same (J, grad); the switch exists for A/B parity runs. */
+int ttm_ctx_set_objgrad_kernel(ttm_ctx* ctx, int mode);
+
 /* ---- component plans -----------------------------------------------------------------------
  * replaces: function_constructor_alternative / function_derivative_constructor_alternative
  * (tm.py:1263-2134): instead of exec'ing generated source, the host compiles the term lists into
  * an int32 blob + a double blob (layout: csrc/ttm_common.cuh, enum H_*), uploaded here.          */
 int ttm_plan_create(ttm_ctx* ctx, const int32_t* host_iblob, int64_t n_int, const double* host_dblob,
                     int64_t n_double, ttm_plan** host_out);
+/* host_info[4] = {in the tile kernel's class (0/1), union of used nonmonotone slots (bit 2*order+hf),
+ *                 monotone terms with an outer product over x_<c, m = m_non + m_mon} */
+int ttm_plan_info(ttm_plan* plan, int* host_info);
 /* re-upload the double blob only (special-term centres/scales move on reset(), tm.py:800) */
 int ttm_plan_update_doubles(ttm_plan* plan, const double* host_dblob, int64_t n_double);
 int ttm_plan_destroy(ttm_plan* plan);
@@ -146,6 +154,18 @@ int ttm_mon_table(ttm_plan* plan, int ntab, double* table, void* stream);
 /* table = [sorted values | abscissae in the same order] (scipy interp1d sorts, assume_sorted=False) */
 int ttm_inverse_table(ttm_plan* plan, double* Xt, int64_t ld, int64_t N, const double* z, const double* table,
                       int ntab, int truncate, void* stream);
+/* K-inv-fused: the whole component loop of inverse_map (tm.py:3684-3698 calling :3987-4084) in one launch for maps
+ * whose nonmonotone terms are constants + per-variable Hermite-function groups of order <= 3 (every other map takes
+ * ttm_inverse_table per component).  Component j = 0..ncomp-1 solves column c0 + j of Xw from the columns before it;
+ * Zt holds its reference samples at Zt + j*ldz; tables = [ncomp][2*ntab] as for ttm_inverse_table; a0[j] = sum of
+ * the constant terms' coefficients.  Apack (ttm_inverse_fused_apack_size doubles) holds coefficient*scale in blocks
+ * of 16 components: block b = rows v = 0 .. c0 + 16 b + 15, row = [16 components][ns slots], zero where variable v is
+ * not a predecessor of the component; ns = 3: slots {He1, He2 e^{-x^2/4}, He3 e^{-x^2/4}}, ns = 6: {He1, He1 e, He2,
+ * He2 e, He3, He3 e}. */
+int ttm_inverse_fused_apack_size(int ncomp, int c0, int ns, int64_t* host_doubles);
+int ttm_inverse_fused(ttm_ctx* ctx, double* Xw, int64_t ld, int64_t N, const double* Zt, int64_t ldz, int ncomp, int c0,
+                      int ns, const double* Apack, const double* a0, const double* tables, int ntab, int truncate,
+                      void* stream);
 /* separable != 0: monotone part is linear in the coefficients; else Gauss-Legendre of the rectifier.
  * host_not_converged receives the number of samples stopped at max_iter (the reference warns).   */
 int ttm_inverse_bisect(ttm_plan* plan, double* Xt, int64_t ld, int64_t N, const double* z, int separable,

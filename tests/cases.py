@@ -205,6 +205,27 @@ def cases():
     return out
 
 
+# ---- headline shapes (BASELINE.json configs C4 / C5 at their real D), fixtures from tests/golden/make_golden_headline.py
+HEADLINE_N = 4000
+HEADLINE_KS = (0, 1, 5, 31, 63)
+HEADLINE_QS = (25, 100)
+C5_INV = dict(D=256, E=128, ntrain=1000, n_table=500, n_bisect=200, seed=4242)
+
+
+def headline_coeffs(mon, non, k):
+    """Seeded coefficient vector [nonmonotone | monotone] of component k for the C4 objective/gradient checks."""
+    rng = np.random.default_rng(7000 + k)
+    return rng.standard_normal(len(non[k]) + len(mon[k])) * 0.05
+
+
+def headline_sep_coeffs(mon, non):
+    """Seeded coefficients of a separable map: nonmonotone N(0, 0.1^2)/sqrt(1+k), monotone positive (0.05 .. 0.55)."""
+    rng = np.random.default_rng(7100)
+    cm = [np.abs(rng.standard_normal(len(mon[k]))) * 0.25 + 0.05 for k in range(len(mon))]
+    cn = [rng.standard_normal(len(non[k])) * 0.1 / np.sqrt(1.0 + k) for k in range(len(mon))]
+    return cm, cn
+
+
 def fresh_kwargs(case):
     """Deep copy of the constructor kwargs (the reference mutates quadrature_input, tm.py:224)."""
     return copy.deepcopy(case['kwargs'])

@@ -1,5 +1,5 @@
-"""Device-time the fused objective+gradient kernel for a few components of the C4 workload.
-Used for tuning (TTM_OBJ_VARIANT / TTM_OBJ_BPS select compiled variants); prints one JSON line."""
+"""Device-time the fused objective+gradient kernel for a few components of the C4 workload; prints one JSON line.
+TTM_KERNEL=general times the general kernel instead of the tile kernel, TTM_GRAM=0 the two-sweep form."""
 import json
 import os
 import sys
@@ -23,11 +23,15 @@ tm = transport_map(X=X, monotone=mon, nonmonotone=non, monotonicity='integrated 
                    quadrature_input={'order': q}, verbose=False)
 rng = np.random.default_rng(0)
 coefs = [rng.standard_normal(len(non[k]) + len(mon[k])) * 0.05 for k in range(D)]
-out = {'variant': os.environ.get('TTM_OBJ_VARIANT', '0'), 'bps': os.environ.get('TTM_OBJ_BPS', '4'), 'n': n, 'q': q}
+general = os.environ.get('TTM_KERNEL', 'tile') == 'general'
+B.check(tm._lib.ttm_ctx_set_objgrad_kernel(tm._ctx, 1 if general else 0))
+bps = int(os.environ.get('TTM_BPS', 0))
+B.check(tm._lib.ttm_ctx_set_blocks_per_sm(tm._ctx, bps))
+out = {'kernel': 'general' if general else 'tile', 'gram': os.environ.get('TTM_GRAM', 'auto'), 'bps': bps, 'n': n, 'q': q}
 stream = tm._stream()
 Xp, ld = B.c_void_p(tm._Xt.data_ptr()), tm._Xt.shape[1]
 for k in (0, 1, 31, 63):
-    tm._gram_nonmon(k)
+    out['k%d_gram' % k] = tm._gram_nonmon(k) is not None
     tm._set_coeffs(k, coefs[k][:len(non[k])], coefs[k][len(non[k]):])
     for _ in range(3):
         B.check(tm._lib.ttm_objgrad_ir_launch(tm._plans[k], Xp, ld, n, stream))

@@ -39,6 +39,8 @@ def lib():
             'ttm_ctx_set_quadrature': [c_void_p, _dp, _dp, c_int],
             'ttm_ctx_set_rectifier': [c_void_p, c_int, c_double],
             'ttm_ctx_set_blocks_per_sm': [c_void_p, c_int],
+            'ttm_ctx_set_objgrad_kernel': [c_void_p, c_int],
+            'ttm_plan_info': [c_void_p, ctypes.POINTER(c_int)],
             'ttm_plan_create': [c_void_p, _ip, c_int64, _dp, c_int64, ctypes.POINTER(c_void_p)],
             'ttm_plan_update_doubles': [c_void_p, _dp, c_int64],
             'ttm_plan_destroy': [c_void_p],
@@ -59,6 +61,9 @@ def lib():
             'ttm_sep_objgrad': [c_void_p, c_void_p, c_int64, c_int64, _dp, _dp, c_void_p],
             'ttm_mon_table': [c_void_p, c_int, c_void_p, c_void_p],
             'ttm_inverse_table': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p],
+            'ttm_inverse_fused_apack_size': [c_int, c_int, c_int, ctypes.POINTER(c_int64)],
+            'ttm_inverse_fused': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_int, c_void_p],
             'ttm_inverse_bisect': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,
                                    ctypes.POINTER(c_int), c_void_p],
             'ttm_density_accumulate': [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int64, c_void_p],

@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char* where) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);          \
     } while (0)
 
-constexpr int MAX_GRID = 148 * 8;
+constexpr int MAX_GRID = 160 * 8;   // rows of the per-plan partials buffer (>= resident blocks of any launch)
 }  // namespace
 
 struct ttm_ctx {
@@ -39,10 +39,12 @@ struct ttm_ctx {
     double wsum = 0.0;
     double* d_xis = nullptr;
     double* d_ws = nullptr;
+    std::vector<double> h_xis, h_ws;   // host copies (kernel-parameter node table of the tile kernel)
     int rect = RECT_EXP;
     double delta = 1e-8;
     int* d_flags = nullptr;   // [0] iter_max, [1] not_converged
     int blocks_per_sm = 0;    // 0: kernel default
+    int force_general = 0;    // 1: K-objgrad always through the general kernel (A/B parity runs)
 };
 
 struct ttm_plan {
@@ -57,7 +59,9 @@ struct ttm_plan {
     double* d_partials = nullptr;  // [MAX_GRID][1+m]
     unsigned int* d_counter = nullptr;
     double* h_pin = nullptr;       // pinned staging [2*(1+m)]
+    cudaEvent_t ev_h2d = nullptr;  // recorded after every H2D copy out of h_pin: the buffer is not rewritten before it
     int gram_mode = 0;
+    int tile_ok = 0, dense_mask = 0, n_out_terms = 0;   // tile-kernel eligibility (parse_view)
 };
 
 extern "C" {
@@ -75,13 +79,16 @@ int ttm_device_sm_count(int device, int* host_sm_count) {
 int ttm_ctx_create(int device, ttm_ctx** host_out) {
     if (!host_out) return fail(TTM_ERR_ARG, "ttm_ctx_create: null output");
     CK(cudaSetDevice(device));
-    auto* c = new ttm_ctx();
-    c->device = device;
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, device));
+    int* d_flags = nullptr;
+    CK(cudaMalloc(&d_flags, 2 * sizeof(int)));
+    cudaError_t e0 = cudaMemset(d_flags, 0, 2 * sizeof(int));
+    if (e0 != cudaSuccess) { cudaFree(d_flags); return cuda_fail(e0, "cudaMemset"); }
+    auto* c = new ttm_ctx();
+    c->device = device;
     c->sm_count = p.multiProcessorCount;
-    CK(cudaMalloc(&c->d_flags, 2 * sizeof(int)));
-    CK(cudaMemset(c->d_flags, 0, 2 * sizeof(int)));
+    c->d_flags = d_flags;
     *host_out = c;
     return TTM_OK;
 }
@@ -106,6 +113,8 @@ int ttm_ctx_set_quadrature(ttm_ctx* c, const double* host_xis, const double* hos
     CK(cudaMemcpy(c->d_xis, host_xis, Q * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_ws, host_ws, Q * sizeof(double), cudaMemcpyHostToDevice));
     c->Q = Q;
+    c->h_xis.assign(host_xis, host_xis + Q);
+    c->h_ws.assign(host_ws, host_ws + Q);
     double s = 0.0;
     for (int q = 0; q < Q; ++q) s += host_ws[q];
     c->wsum = s;
@@ -115,6 +124,12 @@ int ttm_ctx_set_quadrature(ttm_ctx* c, const double* host_xis, const double* hos
 int ttm_ctx_set_blocks_per_sm(ttm_ctx* c, int blocks_per_sm) {
     if (!c || blocks_per_sm < 0 || blocks_per_sm > 8) return fail(TTM_ERR_ARG, "ttm_ctx_set_blocks_per_sm: bad arguments");
     c->blocks_per_sm = blocks_per_sm;
+    return TTM_OK;
+}
+
+int ttm_ctx_set_objgrad_kernel(ttm_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 1) return fail(TTM_ERR_ARG, "ttm_ctx_set_objgrad_kernel: bad arguments");
+    c->force_general = mode;
     return TTM_OK;
 }
 
@@ -150,6 +165,20 @@ static int parse_view(ttm_plan* p, const int32_t* h) {
     if ((v.o_fac_i & 3) || (v.o_ent_i & 3) || (v.o_var_idx & 1) || (v.o_dense_var & 3) || (v.o_d_fac & 3) || (v.o_d_ent & 3))
         return fail(TTM_ERR_ARG, "ttm_plan_create: misaligned record offsets");
     if (v.nslot != 2 * (v.maxord + 1) + v.nst) return fail(TTM_ERR_ARG, "ttm_plan_create: inconsistent slot count");
+    // ---- class of the tile kernel (ttm_objgrad_tile.cu): Hermite-function slots of order 1..3 of x_c, nonmonotone
+    // terms = constants + dense per-variable groups of order <= 3
+    p->n_out_terms = 0;
+    for (int j = 0; j < v.m_mon; ++j) p->n_out_terms += (h[v.o_out_ptr + j] != h[v.o_out_ptr + j + 1]);
+    p->dense_mask = 0;
+    const int dstride = 2 * (v.dense_maxord + 1);
+    for (int e = 0; e < v.ndense * dstride; ++e)
+        if (h[v.o_dense_idx + e] >= 0) p->dense_mask |= 1 << ((e % dstride) & 31);
+    bool ok = v.family == FAM_HERMITE_E && v.nst == 0 && !v.has_plain && v.has_hf && v.maxord >= 1 && v.maxord <= 3 &&
+              v.nvars == 0 && v.nmulti == 0 && v.dense_maxord <= 3 && v.m_mon >= 1 && v.m_mon <= TTM_TILE_MAXMON &&
+              p->n_out_terms <= TTM_TILE_MAXOUT && (p->dense_mask & 3) == 0;
+    for (int s = 0; ok && s < v.nslot; ++s)
+        if (h[v.o_slot_ptr + s] != h[v.o_slot_ptr + s + 1] && !((s & 1) && s >= 3)) ok = false;
+    p->tile_ok = ok ? 1 : 0;
     return TTM_OK;
 }
 
@@ -159,6 +188,13 @@ int ttm_plan_create(ttm_ctx* c, const int32_t* host_iblob, int64_t n_int, const 
     CK(cudaSetDevice(c->device));
     auto* p = new ttm_plan();
     p->ctx = c;
+    // from here on a failing CUDA call frees the partially built plan
+#undef CK
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) { ttm_plan_destroy(p); return cuda_fail(e_, #call); } \
+    } while (0)
     p->n_int = n_int;
     p->n_double = n_double;
     CK(cudaMalloc(&p->d_ib, (n_int + 4) * sizeof(int32_t)));
@@ -176,7 +212,23 @@ int ttm_plan_create(ttm_ctx* c, const int32_t* host_iblob, int64_t n_int, const 
     CK(cudaMemset(p->d_counter, 0, sizeof(unsigned int)));
     CK(cudaMemset(p->d_coeffs, 0, (p->m + 1) * sizeof(double)));
     CK(cudaMallocHost(&p->h_pin, 2 * m1 * sizeof(double)));
+    CK(cudaEventCreateWithFlags(&p->ev_h2d, cudaEventDisableTiming));
     *host_out = p;
+    return TTM_OK;
+#undef CK
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);          \
+    } while (0)
+}
+
+int ttm_plan_info(ttm_plan* p, int* host_info) {
+    if (!p || !host_info) return fail(TTM_ERR_ARG, "ttm_plan_info: null argument");
+    host_info[0] = p->tile_ok;
+    host_info[1] = p->dense_mask;
+    host_info[2] = p->n_out_terms;
+    host_info[3] = p->m;
     return TTM_OK;
 }
 
@@ -193,6 +245,7 @@ int ttm_plan_destroy(ttm_plan* p) {
     cudaFree(p->d_ib); cudaFree(p->d_db); cudaFree(p->d_coeffs); cudaFree(p->d_out);
     cudaFree(p->d_partials); cudaFree(p->d_counter);
     if (p->h_pin) cudaFreeHost(p->h_pin);
+    if (p->ev_h2d) cudaEventDestroy(p->ev_h2d);
     delete p;
     return TTM_OK;
 }
@@ -239,8 +292,10 @@ int ttm_plan_set_coeffs(ttm_plan* p, const double* host_coeffs, void* stream) {
     if (!p || !host_coeffs) return fail(TTM_ERR_ARG, "ttm_plan_set_coeffs: null argument");
     if (p->m == 0) return TTM_OK;
     CK(cudaSetDevice(p->ctx->device));
+    CK(cudaEventSynchronize(p->ev_h2d));          // the previous copy out of h_pin has been consumed
     std::memcpy(p->h_pin, host_coeffs, p->m * sizeof(double));
     CK(cudaMemcpyAsync(p->d_coeffs, p->h_pin, p->m * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaEventRecord(p->ev_h2d, (cudaStream_t)stream));
     return TTM_OK;
 }
 
@@ -259,6 +314,8 @@ static int fill_obj(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, ObjArg
     a.blocks_per_sm = c->blocks_per_sm;
     a.gram_mode = p->gram_mode;
     a.ch_rows = 0;
+    a.h_xis = c->h_xis.data(); a.h_ws = c->h_ws.data();
+    a.tile_ok = (p->tile_ok && !c->force_general) ? 1 : 0; a.dense_mask = p->dense_mask; a.n_out_terms = p->n_out_terms;
     return TTM_OK;
 }
 
@@ -346,9 +403,11 @@ int ttm_sep_objgrad(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const 
     CK(cudaSetDevice(p->ctx->device));
     const int mm = p->view.m_dmon;
     if (mm > p->m) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: inconsistent plan");
+    CK(cudaEventSynchronize(p->ev_h2d));
     std::memcpy(p->h_pin, host_b, mm * sizeof(double));
     double* d_b = p->d_coeffs + p->view.m_non;
     CK(cudaMemcpyAsync(d_b, p->h_pin, mm * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaEventRecord(p->ev_h2d, (cudaStream_t)stream));
     cudaError_t e = ttm_launch_sepobj(p->view, Xt, ld, N, d_b, p->ctx->delta, p->d_partials, p->d_counter, p->d_out,
                                       MAX_GRID, p->ctx->sm_count, (cudaStream_t)stream);
     if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_sep_objgrad: too many monotone terms for shared memory");
@@ -385,6 +444,25 @@ int ttm_inverse_table(ttm_plan* p, double* Xt, int64_t ld, int64_t N, const doub
     a.separable = 1;
     a.table = table; a.ntab = ntab; a.truncate = truncate;
     CK(ttm_launch_inverse_table(a, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_inverse_fused_apack_size(int ncomp, int c0, int ns, int64_t* host_doubles) {
+    if (ncomp <= 0 || c0 < 0 || (ns != 3 && ns != 6) || !host_doubles) return fail(TTM_ERR_ARG, "ttm_inverse_fused_apack_size: bad arguments");
+    *host_doubles = (int64_t)ttm_inverse_fused_apack_doubles(ncomp, c0, ns);
+    return TTM_OK;
+}
+
+int ttm_inverse_fused(ttm_ctx* c, double* Xw, int64_t ld, int64_t N, const double* Zt, int64_t ldz, int ncomp, int c0, int ns,
+                      const double* Apack, const double* a0, const double* tables, int ntab, int truncate, void* stream) {
+    if (!c || !Xw || !Zt || !Apack || !a0 || !tables || N <= 0 || ld < N || ldz < N || ncomp <= 0 || c0 < 0 || ntab < 2)
+        return fail(TTM_ERR_ARG, "ttm_inverse_fused: bad arguments");
+    if (ns != 3 && ns != 6) return fail(TTM_ERR_ARG, "ttm_inverse_fused: ns must be 3 or 6");
+    CK(cudaSetDevice(c->device));
+    InvFusedArgs a;
+    a.Xw = Xw; a.ld = ld; a.N = N; a.Zt = Zt; a.ldz = ldz; a.ncomp = ncomp; a.c0 = c0; a.ns = ns;
+    a.Apack = Apack; a.a0 = a0; a.tables = tables; a.ntab = ntab; a.truncate = truncate;
+    CK(ttm_launch_inverse_fused(a, c->sm_count, (cudaStream_t)stream));
     return TTM_OK;
 }
 

@@ -1,0 +1,233 @@
+// K-inv-fused: the whole triangular solve of inverse_map for a tile of samples in ONE launch
+// (separable monotonicity, table root finder).
+//
+// Reference: inverse_map transport_map.py:3639-3796 loops over the components k on the host and calls
+//            vectorized_root_search_alternate :3987-4084 for each: offset_k = Psi_non(x_<c) a_k  (:4039-4043),
+//            x_c = interp1d(table_k)(z_k - offset_k)                                             (:4047-4076).
+// The per-component kernel (ttm_inverse.cu) re-reads every solved column for every component: sum_k 8 n (k+2)
+// bytes, 64x the algorithmic 8 n (E + 2 (D - E)) at C5 (D = 256, E = 128).  Here a thread keeps its samples and walks
+// the components itself, in blocks of 16:
+//   rectangular part   offsets of the block's 16 components from all variables before the block: per variable the
+//                      Hermite-function features {x, He2 e^{-x^2/4}, He3 e^{-x^2/4}} (one exp) are formed once and
+//                      contracted with the 16 x 3 coefficients, which are staged through shared memory
+//                      (cp.async, double buffered) and read as broadcast LDS.128;
+//   diagonal part      component by component: table look-up (numpy.searchsorted + scipy's interp1d formula),
+//                      store x_c, features of x_c, update of the remaining offsets of the block.
+// Two samples per thread share every coefficient load.  The contraction is FP64-pipe work: 3 FMA per
+// (sample, variable, component) pair, ~73 k FMA per sample at C5; measured FP64 tensor-core (DMMA) peak on B200
+// equals the vector peak (tools/pipe_probe.cu: 37.0 vs 36.4 TFLOP/s), so the contraction stays on the vector pipe
+// where it needs no operand staging of the features.
+//
+// Class: every component in the range has nonmonotone terms = constants + per-variable Hermite-function groups of
+// order <= 3 (the host packs their coefficients, slot mask = the tile kernel's); anything else takes the
+// per-component path.
+#include <cuda_runtime.h>
+
+#include "ttm_common.cuh"
+#include "ttm_exp.cuh"
+#include "ttm_kernels.h"
+
+namespace ttm_invf {
+
+constexpr int TB = 128;       // threads per block
+constexpr int SPT = 2;        // samples per thread
+constexpr int CB = 16;        // components per block
+constexpr int VC = 32;        // variables (coefficient rows) per staged chunk
+
+// features of one variable value, in slot order (NS = 3: {He1, He2 e, He3 e}; NS = 6: {He1, He1 e, He2, He2 e, He3, He3 e})
+template <int NS>
+__device__ __forceinline__ void features(double x, const unsigned int* __restrict__ tab, double (&f)[NS]) {
+    const double xx = x * x;
+    const double ga = ttm_exp32::exp_neg_1(-0.25 * xx, tab);
+    const double P2 = xx - 1.0, P3 = x * (xx - 3.0);
+    if (NS == 3) {
+        f[0] = x; f[1] = P2 * ga; f[2] = P3 * ga;
+    } else {
+        f[0] = x; f[1] = x * ga; f[2] = P2; f[3] = P2 * ga; f[4] = P3; f[NS - 1] = P3 * ga;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// numpy.searchsorted(side='left') + clip + scipy interp1d._call_linear, exactly as inverse_table_kernel
+__device__ __forceinline__ double table_lookup(const double* __restrict__ tab, int ntab, int truncate, double t) {
+    const double tmin = __ldg(tab), tmax = __ldg(tab + ntab - 1);
+    if (truncate) {
+        if (t < tmin) t = tmin;
+        if (t > tmax) t = tmax;
+    }
+    int lo = 0, hi = ntab;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(tab + mid) < t) lo = mid + 1; else hi = mid;
+    }
+    const int k = lo < 1 ? 1 : (lo > ntab - 1 ? ntab - 1 : lo);
+    const double xl = __ldg(tab + k - 1), xh = __ldg(tab + k), yl = __ldg(tab + ntab + k - 1), yh = __ldg(tab + ntab + k);
+    const double den = __dsub_rn(xh, xl);
+    return __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(t, xl), den), yh), __dmul_rn(__ddiv_rn(__dsub_rn(xh, t), den), yl));
+}
+
+// Apack: component block b holds rows v = 0 .. c0 + CB*b + CB - 1, each row CB*NS doubles [jj][slot];
+// entries with v >= c0 + CB*b + jj (not a predecessor of component jj) are zero
+__host__ __device__ inline int64_t block_row0(int b, int c0) { return (int64_t)b * (c0 + CB) + (int64_t)CB * b * (b - 1) / 2; }
+
+template <int NS>
+__global__ void __launch_bounds__(TB) inverse_fused_kernel(const InvFusedArgs a) {
+    extern __shared__ double smem[];
+    constexpr int ROW = CB * NS;                 // doubles per coefficient row
+    unsigned int* s_tab = reinterpret_cast<unsigned int*>(smem);   // exp table (64 words)
+    double* s_coef = smem + 32;                  // [2][VC][ROW]
+    double* s_diag = s_coef + 2 * VC * ROW;      // [CB][ROW]
+    const int tid = threadIdx.x;
+    ttm_exp32::stage_table(s_tab, tid, TB);
+    __syncthreads();
+    const int nblk = (a.ncomp + CB - 1) / CB;
+    const int64_t tiles = (a.N + TB * SPT - 1) / (TB * SPT);
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int64_t i[SPT];
+        bool ok[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            i[s] = tile * (TB * SPT) + s * TB + tid;
+            ok[s] = i[s] < a.N;
+            if (!ok[s]) i[s] = a.N - 1;
+        }
+#pragma unroll 1
+        for (int b = 0; b < nblk; ++b) {
+            const int nrect = a.c0 + CB * b;                      // variables before the block
+            const double* Ab = a.Apack + block_row0(b, a.c0) * ROW;
+            double acc[SPT][CB];
+#pragma unroll
+            for (int s = 0; s < SPT; ++s)
+#pragma unroll
+                for (int jj = 0; jj < CB; ++jj) acc[s][jj] = 0.0;
+            // ---- stage chunk 0 (and the diagonal rows) ----
+            const int nchunk = (nrect + VC - 1) / VC;
+            auto stage = [&](int ch, int buf) {
+                const int r0 = ch * VC;
+                const int nr = min(VC, nrect - r0);
+                const double* src = Ab + (int64_t)r0 * ROW;
+                double* dst = s_coef + buf * VC * ROW;
+                for (int e = tid; e < nr * ROW / 2; e += TB) cp_async16(dst + 2 * e, src + 2 * e);
+            };
+            __syncthreads();                                      // previous block's readers are done
+            {
+                const double* src = Ab + (int64_t)nrect * ROW;
+                for (int e = tid; e < CB * ROW / 2; e += TB) cp_async16(s_diag + 2 * e, src + 2 * e);
+            }
+            if (nchunk > 0) stage(0, 0);
+            cp_async_commit();
+            // ---- rectangular part ----
+            double xn[SPT];
+            if (nrect > 0) {
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) xn[s] = a.Xw[i[s]];
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < nchunk; ++ch) {
+                if (ch + 1 < nchunk) stage(ch + 1, (ch + 1) & 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncthreads();
+                const double* cbuf = s_coef + (ch & 1) * VC * ROW;
+                const int r0 = ch * VC, nr = min(VC, nrect - r0);
+#pragma unroll 1
+                for (int vv = 0; vv < nr; ++vv) {
+                    const int v = r0 + vv;
+                    double f[SPT][NS];
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) features<NS>(xn[s], s_tab, f[s]);
+                    if (v + 1 < nrect) {
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) xn[s] = a.Xw[(int64_t)(v + 1) * a.ld + i[s]];
+                    }
+                    // coefficients of two components at a time: 2 NS doubles = NS broadcast LDS.128 (48 / 96 B aligned)
+                    const double2* c2 = reinterpret_cast<const double2*>(cbuf + vv * ROW);
+#pragma unroll
+                    for (int pr = 0; pr < CB / 2; ++pr) {
+                        double cf[2 * NS];
+#pragma unroll
+                        for (int e = 0; e < NS; ++e) {
+                            const double2 t = c2[pr * NS + e];
+                            cf[2 * e] = t.x;
+                            cf[2 * e + 1] = t.y;
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int q = 0; q < NS; ++q)
+#pragma unroll
+                                for (int s = 0; s < SPT; ++s)
+                                    acc[s][2 * pr + h] = fma(cf[h * NS + q], f[s][q], acc[s][2 * pr + h]);
+                    }
+                }
+                __syncthreads();                                  // buffer (ch & 1) may be overwritten by chunk ch + 2
+            }
+            cp_async_wait<0>();
+            __syncthreads();                                      // diagonal rows landed (nchunk == 0 included)
+            // ---- diagonal part ----
+#pragma unroll
+            for (int jj = 0; jj < CB; ++jj) {
+                const int j = CB * b + jj;
+                if (j < a.ncomp) {
+                    const double* tab = a.tables + (int64_t)j * 2 * a.ntab;
+                    const double a0 = __ldg(a.a0 + j);
+                    double xs[SPT];
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        const double S = acc[s][jj] + a0;                        // offset (:4039-4043)
+                        const double t = __dadd_rn(-S, a.Zt[(int64_t)j * a.ldz + i[s]]);   // target = -offset + Zk (:4071)
+                        xs[s] = table_lookup(tab, a.ntab, a.truncate, t);
+                        if (ok[s]) a.Xw[(int64_t)(a.c0 + j) * a.ld + i[s]] = xs[s];
+                    }
+                    if (jj + 1 < CB && j + 1 < a.ncomp) {
+                        double f[SPT][NS];
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) features<NS>(xs[s], s_tab, f[s]);
+                        const double* crow = s_diag + jj * ROW;
+#pragma unroll
+                        for (int j2 = jj + 1; j2 < CB; ++j2)
+#pragma unroll
+                            for (int q = 0; q < NS; ++q) {
+                                const double c = crow[j2 * NS + q];
+#pragma unroll
+                                for (int s = 0; s < SPT; ++s) acc[s][j2] = fma(c, f[s][q], acc[s][j2]);
+                            }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace ttm_invf
+
+size_t ttm_inverse_fused_apack_doubles(int ncomp, int c0, int ns) {
+    const int nblk = (ncomp + ttm_invf::CB - 1) / ttm_invf::CB;
+    return (size_t)ttm_invf::block_row0(nblk, c0) * ttm_invf::CB * ns;
+}
+
+cudaError_t ttm_launch_inverse_fused(const InvFusedArgs& a, int sm_count, cudaStream_t st) {
+    using namespace ttm_invf;
+    if (a.N == 0 || a.ncomp == 0) return cudaSuccess;
+    if (a.ns != 3 && a.ns != 6) return cudaErrorInvalidValue;
+    const int64_t tiles = (a.N + TB * SPT - 1) / (TB * SPT);
+    int64_t grid = (int64_t)sm_count * 4;
+    if (grid > tiles) grid = tiles;
+    const size_t smem = sizeof(double) * (size_t)(32 + (2 * VC + CB) * CB * a.ns);
+    cudaError_t e;
+    if (a.ns == 3) {
+        if ((e = cudaFuncSetAttribute(inverse_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        inverse_fused_kernel<3><<<(unsigned)grid, TB, smem, st>>>(a);
+    } else {
+        if ((e = cudaFuncSetAttribute(inverse_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        inverse_fused_kernel<6><<<(unsigned)grid, TB, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}

@@ -24,11 +24,24 @@ struct ObjArgs {
     int max_grid;
     int gram_mode;         // 1: nonmonotone gradient slots return h_j = sum_i M_i psi_ij / N (host adds G a)
     int ch_rows;           // rows per chunk (set by the dispatcher)
-    int blocks_per_sm;     // resident blocks per SM of one launch (0: default 4); smaller grids let launches on
+    int blocks_per_sm;     // resident blocks per SM of one launch (0: default); smaller grids let launches on
                            // different streams co-reside on an SM so that their phases overlap
+    // tile kernel (ttm_objgrad_tile.cu): eligibility and table facts computed from the host blob at plan creation
+    int tile_ok;           // 1: order <= 3 Hermite-function component without special/multivariate nonmonotone terms
+    int dense_mask;        // union over the dense groups of the used slots, bit 2*order+hf
+    int n_out_terms;       // monotone terms with an outer product over x_<c
+    const double* h_xis;   // HOST copies of the quadrature rule: the tile kernel's launcher turns them into the
+    const double* h_ws;    // node-constant table it passes as a kernel parameter
+    int tile_lay[16];      // shared-memory layout of the tile kernel (offsets in doubles), computed by its launcher
 };
 
+#define TTM_TILE_MAXMON 8   // monotone terms per component handled by the tile kernel
+#define TTM_TILE_MAXOUT 4   // ... of which with an outer product
+#define TTM_TILE_MAXQ 128   // quadrature nodes (6 constants per node travel as a 6 KB kernel parameter)
+
 cudaError_t ttm_launch_objgrad(const ObjArgs& a, bool grad, int sm_count, cudaStream_t st);
+// tile kernel; cudaErrorNotSupported if the plan is outside its class
+cudaError_t ttm_launch_objgrad_tile(const ObjArgs& a, bool grad, int sm_count, cudaStream_t st);
 
 // column statistics + standardise + transpose (reference: standardize, transport_map.py:750-787)
 cudaError_t ttm_launch_colstats(const double* X, int64_t N, int D, double* mean, double* std, double* scratch,
@@ -86,6 +99,22 @@ struct InvArgs {
     int* iter_max;         // device scalar
     int* not_converged;    // device counter of samples stopped at max_iter
 };
+
+// fused multi-component table inverse (ttm_inverse_fused.cu)
+struct InvFusedArgs {
+    double* Xw;            // working sample matrix, column-major: columns < c0 filled (conditioning block), c0.. written
+    int64_t ld, N;
+    const double* Zt;      // reference samples of component j at Zt + j*ldz
+    int64_t ldz;
+    int ncomp, c0;         // component j solves column c0 + j from the columns < c0 + j
+    int ns;                // slots per (variable, component): 3 = {He1, He2 e, He3 e}, 6 = all plain/HF slots of order 1..3
+    const double* Apack;   // packed coefficient*scale, see ttm_inverse_fused.cu
+    const double* a0;      // [ncomp] constant part of the offset
+    const double* tables;  // [ncomp][2*ntab] sorted values | abscissae
+    int ntab, truncate;
+};
+cudaError_t ttm_launch_inverse_fused(const InvFusedArgs& a, int sm_count, cudaStream_t st);
+size_t ttm_inverse_fused_apack_doubles(int ncomp, int c0, int ns);
 
 cudaError_t ttm_launch_inverse_table(const InvArgs& a, cudaStream_t st);
 cudaError_t ttm_launch_inverse_bisect(const InvArgs& a, cudaStream_t st);

@@ -11,6 +11,11 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a_in, bool grad, int sm_count, cud
     ObjArgs a = a_in;
     const PlanView& P = a.P;
     if (!grad) a.gram_mode = 0;
+    // tile kernel first (ttm_objgrad_tile.cu) when the plan is in its class (a.tile_ok, see ttm_ctx_set_objgrad_kernel)
+    {
+        const cudaError_t e = ttm_launch_objgrad_tile(a, grad, sm_count, st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     if (a.gram_mode && P.dense_maxord > 3) return cudaErrorInvalidValue;   // merged sweep handles orders <= 3
     a.ch_rows = a.gram_mode ? 2 * ttm_obj::RC_SWEEP : ttm_obj::CH_ROWS;
     const int m = P.m_non + P.m_mon;
@@ -31,17 +36,10 @@ cudaError_t ttm_launch_objgrad(const ObjArgs& a_in, bool grad, int sm_count, cud
         return (int)(g < 1 ? 1 : g);
     };
     if (P.nst == 0 && herme && exprect && !P.has_plain && P.maxord <= 3) {
-        // tuning variants of the hot instantiation (RB samples x NQ nodes in flight per thread)
-        static const int variant = getenv("TTM_OBJ_VARIANT") ? atoi(getenv("TTM_OBJ_VARIANT")) : 6;
-        static const int bps_env = getenv("TTM_OBJ_BPS") ? atoi(getenv("TTM_OBJ_BPS")) : 0;
-        const int bps = bps_env > 0 ? bps_env : (a.blocks_per_sm > 0 ? a.blocks_per_sm : 4);
-        switch (variant) {
-            case 0: return ttm_objgrad_cfg0(a, grad, grid_for(bps), smem_for(3), st);
-            case 7: return ttm_objgrad_cfg7(a, grad, grid_for(bps), smem_for(3), st);
-            case 8: return ttm_objgrad_cfg8(a, grad, grid_for(bps), smem_for(3), st);
-            case 9: return ttm_objgrad_cfg9(a, grad, grid_for(bps), smem_for(3), st);
-            default: return ttm_objgrad_cfg6(a, grad, grid_for(bps), smem_for(3), st);  // RB=2 samples x NQ=2 nodes
-        }
+        // general kernel, hot instantiation (RB = 2 samples x NQ = 2 nodes in flight per thread); reached only when the
+        // tile kernel does not cover the plan (special / multivariate nonmonotone terms, nonmonotone order > 3)
+        const int bps = a.blocks_per_sm > 0 ? a.blocks_per_sm : 4;
+        return ttm_objgrad_cfg6(a, grad, grid_for(bps), smem_for(3), st);
     }
     if (P.nst == 0 && herme && exprect && P.maxord <= 3)
         return ttm_objgrad_cfg1(a, grad, grid_for(4), smem_for(3), st);

@@ -543,16 +543,12 @@ cudaError_t launch_cfg(const ObjArgs& a, bool grad, int grid, size_t smem, cudaS
 
 // one exported launcher per instantiation (defined in ttm_objgrad_cfg<N>.cu)
 #define TTM_OBJ_CFG_LIST(X)                          \
-    X(0, 3, false, true, 0, true, true, 2, 1)        \
     X(1, 3, true, true, 0, true, true, 2, 1)         \
     X(2, 6, true, true, 0, true, true, 2, 1)         \
     X(3, 12, true, true, 0, true, true, 1, 1)        \
     X(4, 6, true, true, 0, false, false, 2, 1)       \
     X(5, 20, true, true, 8, false, false, 1, 1)      \
-    X(6, 3, false, true, 0, true, true, 2, 2)        \
-    X(7, 3, false, true, 0, true, true, 4, 1)        \
-    X(8, 3, false, true, 0, true, true, 1, 2)        \
-    X(9, 3, false, true, 0, true, true, 1, 4)
+    X(6, 3, false, true, 0, true, true, 2, 2)
 
 #define TTM_OBJ_DECL(ID, MAXORD, HP, HH, NST, HERME, EXPR, RB, NQ) \
     cudaError_t ttm_objgrad_cfg##ID(const ObjArgs& a, bool grad, int grid, size_t smem, cudaStream_t st);

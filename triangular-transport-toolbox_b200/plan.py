@@ -111,8 +111,11 @@ class _Factors:
         self.ints = []
         self.dbls = []
 
-    def add(self, var, kind, order=0, scale=1.0, scale2=0.0, mu=0.0, sigma=1.0):
-        key = (int(var), int(kind), int(order), float(scale), float(scale2), float(mu), float(sigma))
+    def add(self, var, kind, order=0, scale=1.0, scale2=0.0, mu=0.0, sigma=1.0, ident=None):
+        """`ident` identifies a special term by its position (occurrence slot, cross-term flag) instead of by its
+        centre/scale: those move with the data on reset(), and the tables (indices, blob sizes) must not."""
+        key = (int(var), int(kind), int(order), float(scale), float(scale2)) + \
+              ((float(mu), float(sigma)) if ident is None else ('st',) + tuple(ident))
         if key not in self.index:
             self.index[key] = len(self.ints)
             self.ints.append((int(var), int(kind), int(order), 0))
@@ -148,7 +151,7 @@ class ComponentPlan:
             return [F.add(0, F_ONE)]
         if rec['type'] == 'st':
             mu, sg = self._st_params(rec, special_terms)
-            return [F.add(rec['var'], _ST_KIND[rec['kind']], 0, 1.0, 0.0, mu, sg)]
+            return [F.add(rec['var'], _ST_KIND[rec['kind']], 0, 1.0, 0.0, mu, sg, ident=(rec['slot'], rec['cross']))]
         out = []
         for u, o in zip(rec['vars'], rec['orders']):
             if rec['hf']:
@@ -171,7 +174,7 @@ class ComponentPlan:
             if rec['var'] != c:
                 return [F.add(0, F_ZERO)], -1
             mu, sg = self._st_params(rec, special_terms)
-            return [F.add(c, _ST_DKIND[rec['kind']], 0, 1.0, 0.0, mu, sg)], c
+            return [F.add(c, _ST_DKIND[rec['kind']], 0, 1.0, 0.0, mu, sg, ident=(rec['slot'], rec['cross']))], c
         if c not in rec['vars']:
             return [F.add(0, F_ZERO)], None
         out = []
@@ -358,5 +361,10 @@ class ComponentPlan:
         self.dblob = np.ascontiguousarray(np.concatenate(db), dtype=np.float64)
         self.maxord, self.nst, self.nslot = maxord, nst, nslot
         self.dense_maxord = dense_maxord
+        # host copies of the nonmonotone structure (the fused inverse packs its coefficient matrix from them)
+        self.const_idx = list(const_idx)
+        self.n_slow, self.n_multi = len(var_idx), len(multi_idx)
+        self.dense_groups = [(int(dv[0]), np.asarray(di), np.asarray(ds))
+                             for dv, di, ds in zip(dense_var, dense_idx, dense_scale)]
         self.non_maxvar = non_maxvar
         return self

@@ -117,7 +117,10 @@ class transport_map():
         self.fit_threads = int(fit_threads if fit_threads is not None else _os.environ.get('TTM_FIT_THREADS', 2))
         if fit_threads is None and isinstance(workers, int) and workers > 1:
             self.fit_threads = min(int(workers), 4)     # the reference's process pool becomes host threads + streams
-        self._use_gram = _os.environ.get('TTM_GRAM', '0') != '0'   # experimental one-sweep kernel, see DESIGN.md
+        # Gram mode of K-objgrad (dJ/da = G a + h, one sweep over x_<c per evaluation): on whenever the component is
+        # in the tile kernel's class; TTM_GRAM=0/1 forces it off/on
+        _g = _os.environ.get('TTM_GRAM')
+        self._use_gram = None if _g is None else (_g != '0')
         import threading as _threading
         self._gram_lock = _threading.Lock()
 
@@ -263,6 +266,7 @@ class transport_map():
         if not self.standardize_samples:
             self._Xt = self._to_colmajor(X)
             self._mean_d = self._std_d = None
+            torch.cuda.current_stream(self._device).synchronize()   # worker streams of optimize() read _Xt
             return
         mode = self.standardization.lower()
         if mode == 'standard':
@@ -310,8 +314,14 @@ class transport_map():
     def X(self, value):
         value = np.asarray(value, dtype=np.float64)
         self._Xt = self._to_colmajor(value)
+        self._torch.cuda.current_stream(self._device).synchronize()
         self._N, self._Dtot = value.shape
+        self._N_global = self._N
+        if self._sharded:
+            from .parallel import allreduce_sum
+            self._N_global = int(round(allreduce_sum(np.array([float(self._N)]), self._device)[0]))
         self._X_host = None
+        self._reset_lazy()                     # memoised (J, grad), Gram matrices and lazy Psi belong to the old ensemble
 
     def _column(self, d):
         col = self._Xt[d].cpu().numpy()
@@ -384,6 +394,7 @@ class transport_map():
 
     # ================================================================== plans
     def _compile_plans(self):
+        self._inv_pack_cache = {}
         self._host_plans = []
         for k in range(self.D):
             self._host_plans.append(ComponentPlan(
@@ -391,18 +402,36 @@ class transport_map():
                 self.monotone[k], self.nonmonotone[k], self.special_terms, self.linearization))
         self._free_plans()
         self._plans = []
+        self._plan_info = []
         for p in self._host_plans:
-            h = B.c_void_p()
-            B.check(self._lib.ttm_plan_create(self._ctx, B.iptr(p.iblob), p.iblob.size, B.dptr(p.dblob), p.dblob.size,
-                                              B.ctypes.byref(h)))
-            self._plans.append(h)
+            self._plans.append(self._create_plan(p))
+            self._plan_info.append(self._query_plan(self._plans[-1]))
+
+    def _create_plan(self, p):
+        h = B.c_void_p()
+        B.check(self._lib.ttm_plan_create(self._ctx, B.iptr(p.iblob), p.iblob.size, B.dptr(p.dblob), p.dblob.size,
+                                          B.ctypes.byref(h)))
+        return h
+
+    def _query_plan(self, h):
+        info = (B.c_int * 4)()
+        B.check(self._lib.ttm_plan_info(h, info))
+        return {'tile_ok': bool(info[0]), 'dense_mask': int(info[1]), 'n_out_terms': int(info[2])}
 
     def _refresh_special_terms(self):
-        """Special-term centres/scales moved (reset / precalculate): rebuild the double blobs."""
-        for p, h in zip(self._host_plans, self._plans):
+        """Special-term centres/scales moved (reset / precalculate): rebuild the double blobs.  The int blob does not
+        depend on the data (special-term factors are identified by position, plan._Factors.add); should it ever
+        differ, the plan is re-created instead of indexing stale tables."""
+        for k, p in enumerate(self._host_plans):
             if p.has_special:
+                old = p.iblob
                 p.build(self.special_terms)
-                B.check(self._lib.ttm_plan_update_doubles(h, B.dptr(p.dblob), p.dblob.size))
+                if old.shape == p.iblob.shape and np.array_equal(old, p.iblob):
+                    B.check(self._lib.ttm_plan_update_doubles(self._plans[k], B.dptr(p.dblob), p.dblob.size))
+                else:
+                    self._lib.ttm_plan_destroy(self._plans[k])
+                    self._plans[k] = self._create_plan(p)
+                    self._plan_info[k] = self._query_plan(self._plans[k])
 
     def _free_plans(self):
         if getattr(self, '_plans', None):
@@ -457,6 +486,7 @@ class transport_map():
             self.der_Psi_mon = _LazyList(self.D, lambda k: self._basis(k, 2, self._Xt, self._N))
         self._fg_cache = {}
         self._gram_nn = {}
+        self._gram_donor_G = {}
 
     def reset(self, X):
         """tm.py:710-748."""
@@ -546,19 +576,40 @@ class transport_map():
             ent = self._fg_cache[k] = (key, out)
         return ent[1]
 
+    def _gram_donor(self, k):
+        """Component whose nonmonotone term list starts with component k's list (and is the longest such): its
+        Gram matrix contains G_k as the leading block, so one K-gram launch serves every component of a map whose
+        components share their basis (C4: nonmonotone[k] is a prefix of nonmonotone[D-1]).  Special terms are
+        placed per component (tm.py:2241-2330), so lists containing them are not shared."""
+        spec = self.nonmonotone[k]
+        if any(type(e) == str for e in spec):
+            return k
+        best = k
+        for kk in range(self.D):
+            other = self.nonmonotone[kk]
+            if len(other) > len(self.nonmonotone[best]) and other[:len(spec)] == spec and \
+                    not any(type(e) == str for e in other):
+                best = kk
+        return best
+
     def _gram_nonmon(self, k):
         """G = Psi_non^T Psi_non / N of component k (K-gram, once per ensemble -- the counterpart of the reference's
-        precalculate()).  With it the fused kernel sweeps the columns x_<c once per evaluation instead of twice
-        (dJ/da = G a + mean_i M_i psi_i).  None when the two-sweep kernel is used (TTM_GRAM=0, no nonmonotone
-        terms, or nonmonotone polynomial order > 3).  Off by default: measured slower than two sweeps."""
+        precalculate()).  With it K-objgrad sweeps the columns x_<c once per evaluation instead of twice
+        (dJ/da = G a + mean_i M_i psi_i).  None when the two-sweep form is used (TTM_GRAM=0, no nonmonotone terms,
+        nonmonotone polynomial order > 3, or a component outside the tile kernel's class unless TTM_GRAM=1)."""
         if k in self._gram_nn:
             return self._gram_nn[k]
         with self._gram_lock:
             if k not in self._gram_nn:
                 p = self._host_plans[k]
+                use = self._plan_info[k]['tile_ok'] if self._use_gram is None else self._use_gram
                 G = None
-                if self._use_gram and p.m_non > 0 and p.dense_maxord <= 3:
-                    G = np.ascontiguousarray(self._gram(k)[:p.m_non, :p.m_non]) / self._N_global
+                if use and p.m_non > 0 and p.dense_maxord <= 3:
+                    d = self._gram_donor(k)
+                    if d not in self._gram_donor_G:
+                        md = self._host_plans[d].m_non
+                        self._gram_donor_G[d] = np.ascontiguousarray(self._gram(d)[:md, :md]) / self._N_global
+                    G = np.ascontiguousarray(self._gram_donor_G[d][:p.m_non, :p.m_non])
                     B.check(self._lib.ttm_plan_set_gram_mode(self._plans[k], 1))
                 else:
                     B.check(self._lib.ttm_plan_set_gram_mode(self._plans[k], 0))
@@ -725,11 +776,13 @@ class transport_map():
             import threading
             torch = self._torch
             tls = threading.local()
+            main_stream = torch.cuda.current_stream(self._device)
             B.check(self._lib.ttm_ctx_set_blocks_per_sm(self._ctx, 2))
 
             def run(k):
                 if not hasattr(tls, 'stream'):
                     tls.stream = torch.cuda.Stream(device=self._device)
+                    tls.stream.wait_stream(main_stream)      # the ensemble was produced on the caller's stream
                 with torch.cuda.stream(tls.stream):
                     return k, fit(k, None)
             try:
@@ -783,6 +836,10 @@ class transport_map():
                                    self._std_d[:E].contiguous() if std else None)
             Xw[:E] = Xs
         Zt = self._to_colmajor(Z)
+        fused = self._inverse_fused_setup(comps) if table_mode else None
+        if fused is not None:
+            self._inverse_fused_launch(fused, Xw, Xw.shape[1], N, Zt, Zt.shape[1])
+            comps = []
         for i, k in comps:
             self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
             if table_mode:
@@ -795,6 +852,84 @@ class transport_map():
         else:
             Xout = self._to_rowmajor(Xw[skip:], N, ncol - skip)
         return Xout
+
+    def _monotone_tables(self, comps, start_distance=10, resolution=1001):
+        """Lookup tables of vectorized_root_search_alternate (tm.py:4047-4062) for all listed components in ONE device
+        buffer [ncomp][2*resolution] (values | abscissae) with ONE host round trip: scipy's interp1d sorts its
+        abscissae with a stable sort (assume_sorted=False), which is the identity for a non-decreasing table -- the
+        normal case (monotone coefficients >= 0); only rows that are not sorted are sorted on the host."""
+        pts = np.linspace(-start_distance, start_distance, resolution)
+        tabs = self._empty(len(comps), 2 * resolution)
+        tabs[:, resolution:] = self._upload(pts)
+        for r, (_, k) in enumerate(comps):
+            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+            B.check(self._lib.ttm_mon_table(self._plans[k], resolution, B.c_void_p(tabs[r].data_ptr()), self._stream()))
+        vals = tabs[:, :resolution].cpu().numpy()
+        bad = np.nonzero(~np.all(vals[:, 1:] >= vals[:, :-1], axis=1))[0]
+        for r in bad:
+            ind = np.argsort(vals[r], kind="mergesort")
+            tabs[r] = self._upload(np.concatenate((vals[r][ind], pts[ind])))
+        return tabs
+
+    def _inverse_fused_setup(self, comps, resolution=1001):
+        """Operands of K-inv-fused (ttm_inverse_fused: the component loop of tm.py:3684-3698 in one launch), or None if
+        some component is outside its class (nonmonotone terms other than constants and per-variable Hermite-function
+        groups of order <= 3, components not on consecutive columns)."""
+        if not comps or os.environ.get('TTM_INV_FUSED', '1') == '0':
+            return None
+        from .plan import FAM_HERMITE_E
+        ks = [k for _, k in comps]
+        plans = [self._host_plans[k] for k in ks]
+        c0 = plans[0].c
+        if self._family != FAM_HERMITE_E or any(p.c != c0 + j for j, p in enumerate(plans)):
+            return None
+        if any(p.n_slow or p.n_multi or p.dense_maxord > 3 for p in plans):
+            return None
+        used = set()
+        for p in plans:
+            for _, idx_row, _ in p.dense_groups:
+                used.update(int(s) for s in np.nonzero(idx_row >= 0)[0])
+        if used - {2, 3, 4, 5, 6, 7}:
+            return None
+        slots = [2, 5, 7] if used <= {2, 5, 7} else [2, 3, 4, 5, 6, 7]     # bit 2*order+hf, as in the tile kernel
+        ns, CB, ncomp = len(slots), 16, len(ks)
+        size = B.c_int64()
+        B.check(self._lib.ttm_inverse_fused_apack_size(ncomp, c0, ns, B.ctypes.byref(size)))
+        A = np.zeros(size.value)
+        a0 = np.zeros(ncomp)
+        cache = self.__dict__.setdefault('_inv_pack_cache', {})
+        for j, (k, p) in enumerate(zip(ks, plans)):
+            cn = np.asarray(self.coeffs_nonmon[k], dtype=np.float64)
+            a0[j] = sum(cn[q] for q in p.const_idx)
+            key = (k, c0, j, ns)
+            if key not in cache:                                           # static part of the packing, per component
+                b, jj = divmod(j, CB)
+                row0 = b * (c0 + CB) + CB * b * (b - 1) // 2
+                dst, src, sc = [], [], []
+                for v, idx_row, sc_row in p.dense_groups:
+                    if v >= c0 + j:
+                        cache[key] = None                                  # not a triangular dependency
+                        break
+                    for q, sl in enumerate(slots):
+                        if sl < len(idx_row) and idx_row[sl] >= 0:
+                            dst.append(((row0 + v) * CB + jj) * ns + q)
+                            src.append(int(idx_row[sl]))
+                            sc.append(float(sc_row[sl]))
+                else:
+                    cache[key] = (np.asarray(dst, dtype=np.int64), np.asarray(src, dtype=np.int64), np.asarray(sc))
+            if cache[key] is None:
+                return None
+            dst, src, sc = cache[key]
+            A[dst] = cn[src] * sc
+        return {'ncomp': ncomp, 'c0': c0, 'ns': ns, 'A': self._upload(A), 'a0': self._upload(a0),
+                'tabs': self._monotone_tables(comps, resolution=resolution), 'ntab': resolution}
+
+    def _inverse_fused_launch(self, f, Xw, ld, n, Zt, ldz, stream=None):
+        B.check(self._lib.ttm_inverse_fused(self._ctx, B.c_void_p(Xw.data_ptr()), ld, n, B.c_void_p(Zt.data_ptr()), ldz,
+                                            f['ncomp'], f['c0'], f['ns'], B.c_void_p(f['A'].data_ptr()),
+                                            B.c_void_p(f['a0'].data_ptr()), B.c_void_p(f['tabs'].data_ptr()), f['ntab'],
+                                            1 if self.root_search_truncation else 0,
+                                            stream if stream is not None else self._stream()))
 
     def _monotone_table(self, k, start_distance=10, resolution=1001):
         """The lookup table of vectorized_root_search_alternate (tm.py:4047-4062) for component k (coefficients
@@ -826,10 +961,12 @@ class transport_map():
         N, nz, skip = Z.shape[0], Z.shape[1], self.skip_dimensions
         nout = ncol - skip
         std = self.standardize_samples
+        fused = self._inverse_fused_setup(comps, resolution=resolution)
         tabs = []
-        for _, k in comps:                                   # tables first: they need a host round trip each
-            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
-            tabs.append(self._monotone_table(k, resolution=resolution))
+        if fused is None:
+            for _, k in comps:                               # tables first: they need a host round trip each
+                self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+                tabs.append(self._monotone_table(k, resolution=resolution))
         mean_in = self._mean_d[:E].contiguous() if (std and E > 0) else None
         std_in = self._std_d[:E].contiguous() if (std and E > 0) else None
         mean_out = self._mean_d[skip:].contiguous() if std else None
@@ -885,6 +1022,8 @@ class transport_map():
                         sl['dx'][:n].copy_(sl['hx'][:n], non_blocking=True)
                         B.check(lib.ttm_standardize_transpose(self._ctx, ptr(sl['dx']), n, E, ptr(mean_in), ptr(std_in),
                                                               ptr(sl['Xw']), cap, st))
+                    if fused is not None:
+                        self._inverse_fused_launch(fused, sl['Xw'], cap, n, sl['Zt'], cap, stream=st)
                     for (i, k), tab in zip(comps, tabs):
                         B.check(lib.ttm_inverse_table(self._plans[k], ptr(sl['Xw']), cap, n,
                                                       B.c_void_p(sl['Zt'].data_ptr() + i * cap * 8), ptr(tab),
