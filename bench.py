@@ -38,12 +38,20 @@ METRIC = 'objective+gradient evals/sec at N=1M, K=64'
 UNIT = 'evals/s'
 
 
-def flops_per_eval(k, n, q=Q, m_mon=4):
-    """Algorithmic FP64 work of one eval (frozen instruction costs c_exp=30, c_log=47):
-    node loop Q*(8 + c_exp + m_m + 2 m_m + c_exp + 2 + 1 + 2 m_m) + x_<c part 48 k + epilogue 75, per sample."""
+def flops_per_eval(k, n, q=Q, m_mon=4, c_exp=30):
+    """Algorithmic FP64 work of one eval, SURVEY.md 8(d): node loop Q*(8 + c_exp + m_m + 2 m_m + c_exp + 2 + 1 + 2 m_m)
+    + x_<c part (c_exp + 18) k + epilogue 75 (c_log = 47), per sample.  c_exp = 30 is the survey's frozen cost of the
+    CUDA library exp; c_exp = 18 re-freezes it for the exp the kernel ships (ttm_exp.cuh: 8 FMA + 1 ADD + 1 MUL)."""
     mm = 3 if k == 0 else m_mon
-    node = q * (8 + 30 + mm + 2 * mm + 30 + 2 + 1 + 2 * mm)
-    return n * (node + 48 * k + 75)
+    node = q * (8 + c_exp + mm + 2 * mm + c_exp + 2 + 1 + 2 * mm)
+    return n * (node + (c_exp + 18) * k + 75)
+
+
+def flops_executed(k, n, q=Q):
+    """FP64 flops the shipped tile kernel actually executes per eval (SASS instruction mix, FMA = 2): node loop 31
+    instructions = 24 FMA + 7 MUL/ADD = 55 flop per node; Gram-mode sweep 23 instructions = 14 FMA + 9 = 37 flop per
+    (sample, column); prologue + epilogue (two exp, log, division, slot algebra) ~300 flop per sample."""
+    return n * (55 * q + 37 * k + 300)
 
 
 def bytes_per_eval(k, n):
@@ -97,6 +105,7 @@ class ClockSampler(threading.Thread):
 # CPU arm: the oracle port, component-parallel like the reference's Pool
 # ------------------------------------------------------------------------------------------------
 _OM = None
+_CPU_VALUES = {}
 
 
 def _cpu_eval(args):
@@ -105,7 +114,7 @@ def _cpu_eval(args):
     t = time.perf_counter()
     f = _OM.objective_function(c, k, div)
     g = _OM.objective_function_jacobian(c, k, div)
-    return time.perf_counter() - t, float(f), float(np.linalg.norm(g))
+    return time.perf_counter() - t, k, float(f), np.asarray(g, dtype=np.float64)
 
 
 def cpu_port(n_sample, ks, workers, steps=1, warmup=0):
@@ -121,23 +130,24 @@ def cpu_port(n_sample, ks, workers, steps=1, warmup=0):
                     quadrature_input={'order': Q})
     coefs = coefficients(mon, non)
     work = [(k, coefs[k]) for k in sorted(ks, reverse=True)]      # longest first (tm.py:2821)
-    times = []
+    times, res = [], []
     if workers > 1:
         from multiprocessing import get_context
         with get_context('fork').Pool(workers) as pool:
             for s in range(warmup + steps):
                 t = time.perf_counter()
-                pool.map(_cpu_eval, work, chunksize=1)
+                res = pool.map(_cpu_eval, work, chunksize=1)
                 if s >= warmup:
                     times.append(time.perf_counter() - t)
     else:
         for s in range(warmup + steps):
             t = time.perf_counter()
-            for w in work:
-                _cpu_eval(w)
+            res = [_cpu_eval(w) for w in work]
             if s >= warmup:
                 times.append(time.perf_counter() - t)
     per_step = float(np.mean(times))
+    global _CPU_VALUES
+    _CPU_VALUES = {k: (f, g) for _, k, f, g in res}               # oracle (J, grad) per component: the parity leg
     return len(ks) / per_step * (n_sample / N_FULL), per_step
 
 
@@ -205,18 +215,71 @@ def inverse_metric(rank, world, dist, torch, with_cpu=False):
         if not alt:
             resid = float(np.max(np.abs(tm.map(Xs[:20000])[:, E:] - Z[:20000])))
             res[mode]['max_residual'] = resid
+    # ---- device-resident rate of the fused triangular solve (K-inv-fused) and its roofline
+    comps = [(i, k) for i, k in enumerate(range(E, Dm))]
+    fused = tm._inverse_fused_setup(comps)
+    dev = None
+    if fused is not None:
+        g = torch.Generator(device='cuda').manual_seed(rank)
+        Xw = torch.zeros(Dm, ns, dtype=torch.float64, device='cuda')
+        Xw[:E] = torch.randn(E, ns, dtype=torch.float64, device='cuda', generator=g)
+        Zt = torch.randn(Dm - E, ns, dtype=torch.float64, device='cuda', generator=g)
+        ts = []
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tm._inverse_fused_launch(fused, Xw, ns, ns, Zt, ns)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t_dev = torch.tensor([float(np.mean(ts[1:]))], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        t_dev = float(t_dev[0])
+        alg_bytes = 8 * ns * (E + 2 * (Dm - E))                         # X* in, Z in, X out
+        pairs = sum(k for k in range(E, Dm))                            # (variable, component) pairs per sample
+        fl = ns * (2 * 3 * pairs + 30 * (Dm - E))                       # 3 FMA per pair + interpolation
+        dev = {'samples_per_s': ns * world / t_dev, 'seconds': t_dev,
+               'roofline': {'bound': 'fp64', 'achieved': fl / t_dev / 1e12, 'unit': 'TFLOP/s',
+                            'flops_per_sample': fl / ns, 'algorithmic_bytes': alg_bytes,
+                            'algorithmic_gbs': alg_bytes / t_dev / 1e9,
+                            'how': 'K-inv-fused, inputs resident in HBM, CUDA events; flops = 3 FMA per (sample, variable, '
+                                   'component) pair of the triangular contraction (exp of the features not counted)'}}
+        del Xw, Zt
     cpu = None
+    parity = None
     if with_cpu and rank == 0 and world == 1:
-        cpu = inverse_cpu_port(tm, mon, non, Dm, E)
+        cpu, parity = inverse_cpu_port(tm, mon, non, Dm, E)
+    coef_check = None
+    if world > 1:
+        coef_check = coefficients_identical_across_ranks(tm, dist, torch)
     out = {'metric': 'inverse_map samples/sec', 'value': res['table']['samples_per_s'], 'unit': 'samples/s',
             'config': {'workload': 'C5: D=256 separable map, conditional sampling with E=128, %d samples per GPU, '
                                    'default table root finder (alternate_root_finding=True); steady state (second full-size call)' % ns,
                        'n_train': ntrain},
             'bisection': res['bisection'], 'table': res['table'], 'ctor_s': ctor_s, 'optimize_s': opt_s,
             'scaling': 'weak', 'e2e': True}
+    if dev is not None:
+        out['device'] = dev
     if cpu is not None:
         out['cpu_baseline'] = cpu
+        out['parity_max_abs'] = parity
+    if coef_check is not None:
+        out['coefficients_identical_across_ranks'] = coef_check
     return out
+
+
+def coefficients_identical_across_ranks(tm, dist, torch):
+    """After optimize() every rank must hold bit-identical coefficient lists (one all-gather of the fitted shards)."""
+    import hashlib
+    h = hashlib.sha256()
+    for k in range(tm.D):
+        h.update(np.ascontiguousarray(tm.coeffs_nonmon[k], dtype=np.float64).tobytes())
+        h.update(np.ascontiguousarray(tm.coeffs_mon[k], dtype=np.float64).tobytes())
+    mine = torch.tensor(list(h.digest()), dtype=torch.uint8, device='cuda')
+    allh = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(allh, mine)
+    return bool(all(torch.equal(allh[0], x) for x in allh))
 
 
 def inverse_cpu_port(tm, mon, non, Dm, E, ntrain=2000, n_table=2000):
@@ -237,11 +300,47 @@ def inverse_cpu_port(tm, mon, non, Dm, E, ntrain=2000, n_table=2000):
     Z = rng.standard_normal((n_table, Dm - E))
     om.alternate_root_finding = True         # the default root finder (the oracle's bisection arm has ~60 s of fixed
     t = time.perf_counter()                  # cost per call at D=256 and is left to the parity tests)
-    om.inverse_map(Z, X_star=Xstar)
+    Xo = om.inverse_map(Z, X_star=Xstar)
     v = n_table / (time.perf_counter() - t)
-    return {'value': v, 'unit': 'samples/s', 'cores': 1, 'kind': 'port',
-            'sample': 'oracle inverse_map of the same C5 map (coefficients from the GPU fit, oracle built on %d training '
-                      'samples): %d conditional samples, table root finder, single process' % (ntrain, n_table)}
+    # parity leg: a GPU map built on the SAME training subset as the oracle (same standardisation and special-term
+    # placement), same coefficients, same inputs
+    from transport_map import transport_map
+    tg = transport_map(X=synthetic_samples(ntrain, Dm, seed=0), monotone=mon, nonmonotone=non,
+                       monotonicity='separable monotonicity', verbose=False)
+    for k in range(Dm):
+        tg.coeffs_nonmon[k] = np.array(tm.coeffs_nonmon[k], dtype=np.float64)
+        tg.coeffs_mon[k] = np.array(tm.coeffs_mon[k], dtype=np.float64)
+    Xg = tg.inverse_map(Z.copy(), X_star=Xstar.copy())
+    del tg
+    parity = float(np.max(np.abs(Xg - Xo)))
+    return ({'value': v, 'unit': 'samples/s', 'cores': 1, 'kind': 'port',
+             'sample': 'oracle inverse_map of the same C5 map (coefficients from the GPU fit, oracle built on %d training '
+                       'samples): %d conditional samples, table root finder, single process' % (ntrain, n_table)}, parity)
+
+
+def multi_gpu_check(rank, world, dist, torch):
+    """Sample-sharded evaluation (the K < #GPUs path of SURVEY 8(e): every rank holds N/world rows, (J, grad) are
+    all-reduced) against the same evaluation on the whole ensemble held by one rank (the component-sharded layout)."""
+    from transport_map import transport_map
+    Dm, n = 8, 64 * 1024
+    X = synthetic_samples(n, Dm, seed=5)
+    mon, non = c4_terms(Dm)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='integrated rectifier', quadrature_input={'order': 25},
+              verbose=False)
+    full = transport_map(X=X.copy(), **kw)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    shard = transport_map(X=X[lo:hi].copy(), sample_sharded=True, **kw)
+    rng = np.random.default_rng(9)
+    worst = 0.0
+    for k in (0, 3, 7):
+        c = rng.standard_normal(len(non[k]) + len(mon[k])) * 0.1
+        div = len(non[k])
+        f0, g0 = full.objective_function(c, k, div), full.objective_function_jacobian(c, k, div)
+        f1, g1 = shard.objective_function(c, k, div), shard.objective_function_jacobian(c, k, div)
+        worst = max(worst, abs(f0 - f1) / max(1.0, abs(f0)), float(np.max(np.abs(g0 - g1) / np.maximum(1.0, np.abs(g0)))))
+    w = torch.tensor([worst], dtype=torch.float64, device='cuda')
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    return {'sample_sharded_vs_whole_max_rel': float(w[0]), 'ranks': world, 'rows_per_rank': hi - lo}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -274,8 +373,16 @@ def run_gpu(args):
     mine = shard_components(list(range(D)), rank, world)
     lib, stream = tm._lib, tm._stream()
     Xp, ld = B.c_void_p(tm._Xt.data_ptr()), tm._Xt.shape[1]
+    # Gram matrix G = Psi_non^T Psi_non / N of the ensemble (K-gram, ONE launch for the map: every component's G is a
+    # leading block of the last component's): once per ensemble like the reference's precalculate(); with it an
+    # evaluation sweeps the columns x_<c once (dJ/da = G a + h).  Timed separately, not part of the evaluations.
+    torch.cuda.synchronize()
+    t_g = time.perf_counter()
     for k in mine:
-        tm._gram_nonmon(k)                          # no-op unless TTM_GRAM=1 (experimental one-sweep kernel)
+        tm._gram_nonmon(k)
+    torch.cuda.synchronize()
+    gram_setup_s = time.perf_counter() - t_g
+    for k in mine:
         tm._set_coeffs(k, coefs[k][:len(non[k])], coefs[k][len(non[k]):])
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')   # 512 MB > 126 MB L2
 
@@ -285,7 +392,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    NSTREAMS = 2
+    NSTREAMS = args.streams
     streams = [torch.cuda.Stream() for _ in range(NSTREAMS)]
     sptr = [B.c_void_p(st_.cuda_stream) for st_ in streams]
 
@@ -319,7 +426,7 @@ def run_gpu(args):
             if rep > 0:
                 per_k[k].append(ea.elapsed_time(eb) * 1e-3)
     # ---- value: inputs resident in HBM, device time only
-    B.check(lib.ttm_ctx_set_blocks_per_sm(tm._ctx, 2))
+    B.check(lib.ttm_ctx_set_blocks_per_sm(tm._ctx, args.bps))
     for _ in range(args.warmup):
         e0 = torch.cuda.Event()
         e0.record()
@@ -382,6 +489,31 @@ def run_gpu(args):
     sampler.stop()
 
     fp64_peak_tflops = tm.fp64_peak_tflops() if rank == 0 else 0.0
+
+    # ---- end-to-end fit of the north-star map: optimize() of all 64 components at N = 1M, Q = 100 (components sharded
+    # over the ranks, one all-gather of the coefficients), wall clock, max over ranks
+    fit = None
+    if not args.no_fit:
+        barrier()
+        t_f = time.perf_counter()
+        tm.optimize()
+        torch.cuda.synchronize()
+        t_fit_local = time.perf_counter() - t_f
+        gmax = 0.0
+        for k in mine[:2] + mine[-1:]:
+            c = np.concatenate((tm.coeffs_nonmon[k], tm.coeffs_mon[k]))
+            gmax = max(gmax, float(np.max(np.abs(tm.objective_function_jacobian(c, k, len(tm.coeffs_nonmon[k]))))))
+        tf = torch.tensor([t_fit_local, gmax], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fit = {'optimize_wall_s': float(tf[0]), 'max_abs_gradient_at_solution': float(tf[1]),
+               'fit_s_rank0': tm._last_timing['fit_s'], 'gather_s_rank0': tm._last_timing['gather_s'],
+               'components_rank0': tm._last_timing['components'], 'gram_setup_s': gram_setup_s,
+               'fit_threads': tm.fit_threads}
+        if world > 1:
+            fit['coefficients_identical_across_ranks'] = coefficients_identical_across_ranks(tm, dist, torch)
+    multi = multi_gpu_check(rank, world, dist, torch) if world > 1 else None
+
     tt = torch.tensor([t_local, t_e2e_local], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -402,33 +534,53 @@ def run_gpu(args):
         by = sum(bytes_per_eval(k, n) for k in mine)
         t_kernels = t_local / args.steps            # the step is 64 launches of this one kernel (2 streams)
         t_seq = sum(kt.values())
-        fp64_peak = fp64_peak_tflops
+        # FP64 peak: the tracked measurement of tools/pipe_probe.cu on this pool (profiles/fp64_peaks_r2.json, written
+        # once with its clock record); the live probe of this run is reported beside it
+        peaks_fp64 = {}
+        try:
+            peaks_fp64 = json.load(open(os.path.join(ROOT, 'profiles', 'fp64_peaks_r2.json')))
+        except Exception:
+            pass
+        fp64_peak = float(peaks_fp64.get('dfma_tflops', fp64_peak_tflops))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic_r2.json')))
+        except Exception:
+            pass
+        fl18 = sum(flops_per_eval(k, n, c_exp=18) for k in mine)
+        flx = sum(flops_executed(k, n) for k in mine)
         achieved = fl / t_kernels / 1e12
+        per_launch_traffic = traffic.get('per_launch_avg_bytes') if (n == N_FULL and world == 1) else None
         roofline = {
             'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of the 64 launches of one step (N=1M, 1 GPU), per launch:
-            # 32.87 GB read + 2.97 GB written / 64.  Algorithmic: 8 N (k+1), 260 MB on average -- the kernel sweeps
-            # the columns x_<c twice (value, gradient); the writes are the spilled node-loop state.
-            'traffic': 5.60e8 if (n == N_FULL and world == 1) else None,
-            'traffic_ncu': {'per_launch_avg_bytes': 5.60e8, 'k63_bytes': 1.10e9, 'k0_bytes': 2.4e7,
-                            'algorithmic_per_launch_avg_bytes': 2.60e8,
-                            'source': 'profiles/ncu_traffic_64launches_r1.csv (ncu --metrics dram__bytes_read.sum,'
-                                      'dram__bytes_write.sum over the 64 launches of one bench step, N=1M)'},
-            'peak_source': 'ttm_fp64_peak: dependent-free DFMA chains, measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
+            'traffic': per_launch_traffic,
+            'traffic_source': traffic.get('source'),
+            'peak_source': 'profiles/fp64_peaks_r2.json: tools/pipe_probe.cu dependent-free DFMA chains, %s MHz '
+                           '(MEASURED_PEAKS.json has no FP64 figure); DMMA peak %s TFLOP/s' % (
+                               peaks_fp64.get('clock_rate_mhz'), peaks_fp64.get('dmma_m8n8k4_tflops')),
+            'peak_live_probe': fp64_peak_tflops,
+            # the same time against two other flop counts: the survey formula re-frozen for the
+            # shipped exp (c_exp = 18 instead of the library's 30), and the flops the shipped SASS executes
+            'achieved_refrozen': fl18 / t_kernels / 1e12, 'frac_refrozen': fl18 / t_kernels / 1e12 / fp64_peak,
+            'achieved_executed': flx / t_kernels / 1e12, 'frac_executed': flx / t_kernels / 1e12 / fp64_peak,
+            'ncu_pipe_fp64_active_pct': traffic.get('pipe_fp64_active_pct'),
             'flops_per_launch_avg': fl / len(mine), 'bytes_per_launch_avg': by / len(mine),
             'launch_ms_avg': t_kernels / len(mine) * 1e3,
             'launch_ms_avg_sequential': t_seq / len(mine) * 1e3,
-            'how': 'achieved = algorithmic flops of the step / CUDA-event step time (launches overlap on 2 streams); '
-                   'per_k = isolated sequential launches with the default grid',
+            'how': 'achieved = algorithmic flops of the step (SURVEY 8(d), frozen c_exp = 30) / CUDA-event step time '
+                   '(launches overlap on %d streams); per_k = isolated sequential launches with the default grid' % NSTREAMS,
             'hbm': {'achieved_gbs': by / t_kernels / 1e9, 'peak_gbs': hbm_peak, 'frac': by / t_kernels / 1e9 / hbm_peak,
                     'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback'},
             'per_k': {str(k): {'ms': kt[k] * 1e3, 'tflops': flops_per_eval(k, n) / kt[k] / 1e12,
+                               'frac': flops_per_eval(k, n) / kt[k] / 1e12 / fp64_peak,
+                               'tflops_refrozen': flops_per_eval(k, n, c_exp=18) / kt[k] / 1e12,
+                               'tflops_executed': flops_executed(k, n) / kt[k] / 1e12,
                                'evals_per_s': 1.0 / kt[k]} for k in (0, 31, 63) if k in kt},
         }
         line = {
@@ -438,28 +590,50 @@ def run_gpu(args):
             'config': {'workload': 'C4: synthetic D=64 integrated-rectifier map, order-3 Hermite functions, Q=%d, N=%d' % (Q, n),
                        'components': D, 'samples': n, 'quadrature_order': Q, 'parallelism': 'components sharded over %d GPU(s)' % world,
                        'l2': 'flushed between timed steps (512 MB write); the sample matrix itself is %d MB' % (8 * n * D >> 20),
-                       'issue': '64 independent evaluations per step on 2 CUDA streams, 2 resident blocks per SM per launch'},
+                       'issue': '64 independent evaluations per step on %d CUDA stream(s), %d resident block(s) per SM per launch; '
+                                'Gram matrix of the ensemble precomputed once (%.3f s, not in the timed region)' % (
+                                    NSTREAMS, args.bps, gram_setup_s)},
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': int(sum(8 * len(coefs[k]) for k in range(D))),
                     'd2h_bytes_per_step': int(sum(8 * (1 + len(coefs[k])) for k in range(D))),
                     'api': 'transport_map.objective_function + objective_function_jacobian per component (host numpy in/out), '
-                           'called from 2 host threads like optimize()'},
+                           'called from %d host threads like optimize()' % NSTREAMS},
             'gpu_launches': D * args.steps,
             'roofline': roofline,
             'clocks': sampler.summary(),
             'wall_s_value_region': wall_value,
         }
+        if fit is not None:
+            line['fit'] = fit
+            line['optimize_wall_s'] = fit['optimize_wall_s']
+        if multi is not None:
+            line['multi_gpu_check'] = multi
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             ks = [0, 31, 63]
             n_cpu = 20000
             v, per = cpu_port(n_cpu, ks, 1)
+            # parity leg: the GPU map on the same rows and coefficients against the oracle values just computed
+            tg = transport_map(X=synthetic_samples(n_cpu, D, seed=0), monotone=mon, nonmonotone=non,
+                               polynomial_type='hermite function', monotonicity='integrated rectifier',
+                               quadrature_input={'order': Q}, verbose=False)
+            worst = 0.0
+            for k in ks:
+                fo, go = _CPU_VALUES[k]
+                fg = tg.objective_function(coefs[k], k, len(non[k]))
+                gg = tg.objective_function_jacobian(coefs[k], k, len(non[k]))
+                worst = max(worst, abs(fg - fo) / max(1.0, abs(fo)), float(np.max(np.abs(gg - go) / np.maximum(1.0, np.abs(go)))))
+            del tg
+            line['parity'] = {'objgrad_max_rel': worst,
+                              'objgrad_sample': 'J and grad J of k=0,31,63 on the CPU leg\'s %d rows, GPU (tile kernel, Gram mode) vs oracle' % n_cpu}
             line['cpu_baseline'] = {
                 'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                 'sample': 'components k=0,31,63 of the same C4 map on %d samples (single process, BLAS threads = %s), '
                           'evals/s scaled linearly to N=1M; host has %d cores' % (n_cpu, os.environ.get('OPENBLAS_NUM_THREADS'), cores)}
         if inv is not None:
             line['inverse_map'] = inv
+            if 'parity_max_abs' in inv:
+                line.setdefault('parity', {})['inverse_max_abs'] = inv['parity_max_abs']
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line))
@@ -477,6 +651,9 @@ def main():
     ap.add_argument('--n', type=int, default=N_FULL, help='samples (default: the metric point, 1M)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-inverse', action='store_true', help='skip the secondary inverse_map metric (config C5)')
+    ap.add_argument('--no-fit', action='store_true', help='skip the end-to-end optimize() of the C4 map')
+    ap.add_argument('--streams', type=int, default=2, help='CUDA streams the evaluations of a step are issued on')
+    ap.add_argument('--bps', type=int, default=2, help='resident blocks per SM of one launch (x streams = blocks per SM)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

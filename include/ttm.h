@@ -131,6 +131,19 @@ int ttm_density_accumulate(ttm_ctx* ctx, double* acc, const double* S, const dou
 int ttm_density_finish(ttm_ctx* ctx, const double* acc, const double* log_target, double* out, int64_t N,
                        void* stream);
 
+/* K-map-fused / K-pullback: all D components of a (small) separable map on row-major samples in ONE launch.
+ * replaces: map tm.py:2391-2437 + the whole of evaluate_pullback_density :2646-2712 / the log-determinant loop of
+ * evaluate_pushforward_density :2618-2644 (the per-component entry points above remain for large maps).
+ * host_plans[D]: the components, coefficients as last set with ttm_plan_set_coeffs; host_sigma[D]: the X_std entry
+ * dividing d_k S_k (the reference uses X_std[k] in the pullback and X_std[k+skip] in the pushforward);
+ * X: device row-major (n, Dtot) UNstandardised samples; mean/std: device [Dtot] or both NULL.
+ *   mode 0: out[i] = pullback density, Z (optional, row-major (n, D)) = map output
+ *   mode 1: out[i] = exp(log_target[i] - sum_k log(d_k S_k / sigma_k))
+ *   mode 2: Z = map output only */
+int ttm_map_fused(ttm_ctx* ctx, ttm_plan* const* host_plans, int D, const double* host_sigma, const double* X, int64_t n,
+                  int Dtot, const double* mean, const double* std, const double* log_target, int mode, double* Z,
+                  double* out, void* stream);
+
 /* ---- K-gram (FP64 tensor-core DMMA) ----------------------------------------------------------
  * replaces: the dense contractions of worker_task_monotone, tm.py:2966-2975 (QR / A_sqrt) and
  * :3031-3050 (ridge normal equations).  G = [Psi_non | Psi_mon]^T [Psi_non | Psi_mon], row-major

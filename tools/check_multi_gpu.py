@@ -55,6 +55,14 @@ e_grad = rel(ts.objective_function_jacobian(c, 3, len(non[3])), single.objective
 ts.optimize()
 flat2 = np.concatenate([np.concatenate((ts.coeffs_nonmon[k], ts.coeffs_mon[k])) for k in range(D)])
 e_samp = rel(flat2, flat1)
+# (c) map() / inverse_map() shard by samples with no exchange: every rank maps its own rows
+for k in range(D):
+    ts.coeffs_nonmon[k], ts.coeffs_mon[k] = single.coeffs_nonmon[k].copy(), single.coeffs_mon[k].copy()
+Zfull = single.map(X.copy())
+e_map = rel(ts.map(X[lo:hi].copy()), Zfull[lo:hi])
+Zr = np.random.default_rng(11).standard_normal((2048, D))
+r0, r1 = rank * 2048 // world, (rank + 1) * 2048 // world
+e_inv = float(np.max(np.abs(ts.inverse_map(Zr[r0:r1].copy()) - single.inverse_map(Zr.copy())[r0:r1])))
 # separable + L2 (Gram all-reduce)
 mon6, non6 = ex06_terms(3)
 X6 = np.column_stack((X[:, 0] + 0.3 * X[:, 1], X[:, :3]))
@@ -69,8 +77,22 @@ s2 = transport_map(X=X6[lo:hi].copy(), sample_sharded=True, **kw6)
 s2.optimize()
 e_sep = max(rel(s2.coeffs_mon[k], s1.coeffs_mon[k]) for k in range(3))
 e_sep = max(e_sep, max(rel(s2.coeffs_nonmon[k], s1.coeffs_nonmon[k]) for k in range(3)))
+# pullback density, sample-sharded (fused small-map kernel) against the whole-ensemble map
+for k in range(3):
+    s2.coeffs_nonmon[k], s2.coeffs_mon[k] = s1.coeffs_nonmon[k].copy(), s1.coeffs_mon[k].copy()
+e_dens = rel(s2.evaluate_pullback_density(X6[lo:hi, 1:].copy(), X_star=X6[lo:hi, :1].copy()),
+             s1.evaluate_pullback_density(X6[:, 1:].copy(), X_star=X6[:, :1].copy())[lo:hi])
+errs = torch.tensor([e_comp, e_obj, e_grad, e_samp, e_sep, e_map, e_inv, e_dens], dtype=torch.float64, device='cuda')
+dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+e_comp, e_obj, e_grad, e_samp, e_sep, e_map, e_inv, e_dens = [float(v) for v in errs]
 if rank == 0:
-    print('MULTI_GPU_CHECK world=%d component_sharded=%.2e sample_sharded: obj=%.2e grad=%.2e coeffs=%.2e separable=%.2e'
-          % (world, e_comp, e_obj, e_grad, e_samp, e_sep))
+    line = ('MULTI_GPU_CHECK world=%d component_sharded=%.2e sample_sharded: obj=%.2e grad=%.2e coeffs=%.2e separable=%.2e '
+            'map=%.2e inverse=%.2e pullback=%.2e' % (world, e_comp, e_obj, e_grad, e_samp, e_sep, e_map, e_inv, e_dens))
+    print(line)
+    out = os.environ.get('TTM_MULTI_GPU_LOG')
+    if out:
+        with open(out, 'a') as f:
+            f.write(line + '\n')
 assert e_comp == 0.0 and e_obj < 1e-12 and e_grad < 1e-11 and e_samp < 1e-6 and e_sep < 1e-6
+assert e_map < 1e-9 and e_inv < 2e-8 and e_dens < 1e-9
 dist.destroy_process_group()

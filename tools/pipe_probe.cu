@@ -14,6 +14,16 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
+// SM clock actually running during the probe: clock64 ticks of one block over a cudaEvent-timed kernel
+__global__ void k_clock(long long* ticks, double* sink, int iters) {
+    const long long t0 = clock64();
+    double a = threadIdx.x * 1e-3;
+    for (int it = 0; it < iters; ++it) a = fma(a, 1.0000001, 1e-9);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) ticks[0] = t1 - t0;
+    if (a == 123.456) sink[0] = a;
+}
+
 template <int NINT, bool LDS>
 __global__ void k_dfma(double* sink, int iters) {
     __shared__ double tab[256];
@@ -126,6 +136,17 @@ int main() {
     const int sm = p.multiProcessorCount, block = 256, grid = sm * 8, iters = 1 << 14;
     const double threads = (double)grid * block;
     printf("{\"gpu\": \"%s\", \"sm_count\": %d, \"clock_rate_mhz\": %.0f", p.name, sm, clk_khz / 1e3);
+    {
+        // warm the clocks with ~1 s of DFMA work, then measure the SM clock seen by a long dependent chain
+        for (int rep = 0; rep < 200; ++rep) k_dfma<0, false><<<grid, block>>>(sink, iters);
+        CK(cudaDeviceSynchronize());
+        long long* ticks;
+        CK(cudaMalloc(&ticks, 8));
+        const double ms = time_ms([&] { k_clock<<<sm, block>>>(ticks, sink, 1 << 20); });   // one wave: block 0 spans the kernel
+        long long h = 0;
+        CK(cudaMemcpy(&h, ticks, 8, cudaMemcpyDeviceToHost));
+        printf(", \"sm_clock_mhz_under_load\": %.0f", h / (ms * 1e-3) / 1e6);
+    }
     {
         const double ms = time_ms([&] { k_dfma<0, false><<<grid, block>>>(sink, iters); });
         printf(", \"dfma_tflops\": %.3f", 2.0 * 8 * iters * threads / (ms * 1e-3) / 1e12);

@@ -45,6 +45,10 @@ struct ttm_ctx {
     int* d_flags = nullptr;   // [0] iter_max, [1] not_converged
     int blocks_per_sm = 0;    // 0: kernel default
     int force_general = 0;    // 1: K-objgrad always through the general kernel (A/B parity runs)
+    FusedComp* d_fused = nullptr;   // component table of ttm_map_fused (device) and its pinned host mirror
+    FusedComp* h_fused = nullptr;
+    int fused_cap = 0;
+    cudaEvent_t ev_fused = nullptr;
 };
 
 struct ttm_plan {
@@ -99,6 +103,9 @@ int ttm_ctx_destroy(ttm_ctx* c) {
     cudaFree(c->d_xis);
     cudaFree(c->d_ws);
     cudaFree(c->d_flags);
+    cudaFree(c->d_fused);
+    if (c->h_fused) cudaFreeHost(c->h_fused);
+    if (c->ev_fused) cudaEventDestroy(c->ev_fused);
     delete c;
     return TTM_OK;
 }
@@ -384,6 +391,41 @@ int ttm_density_finish(ttm_ctx* c, const double* acc, const double* log_target, 
     if (!c || !acc || !out || N <= 0) return fail(TTM_ERR_ARG, "ttm_density_finish: bad arguments");
     CK(cudaSetDevice(c->device));
     CK(ttm_launch_density_finish(acc, log_target, out, N, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_map_fused(ttm_ctx* c, ttm_plan* const* host_plans, int D, const double* host_sigma, const double* X, int64_t n,
+                  int Dtot, const double* mean, const double* sd, const double* log_target, int mode, double* Z, double* out,
+                  void* stream) {
+    if (!c || !host_plans || D <= 0 || !X || n <= 0 || Dtot <= 0 || mode < 0 || mode > 2 || (mode != 2 && (!out || !host_sigma)) ||
+        (mode == 2 && !Z) || ((mean == nullptr) != (sd == nullptr)))
+        return fail(TTM_ERR_ARG, "ttm_map_fused: bad arguments");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D > c->fused_cap) {
+        cudaFree(c->d_fused);
+        if (c->h_fused) cudaFreeHost(c->h_fused);
+        c->d_fused = nullptr; c->h_fused = nullptr; c->fused_cap = 0;
+        CK(cudaMalloc(&c->d_fused, D * sizeof(FusedComp)));
+        CK(cudaMallocHost(&c->h_fused, D * sizeof(FusedComp)));
+        if (!c->ev_fused) CK(cudaEventCreateWithFlags(&c->ev_fused, cudaEventDisableTiming));
+        c->fused_cap = D;
+    }
+    CK(cudaEventSynchronize(c->ev_fused));                       // previous upload out of h_fused consumed
+    for (int k = 0; k < D; ++k) {
+        if (!host_plans[k] || host_plans[k]->ctx != c) return fail(TTM_ERR_ARG, "ttm_map_fused: plan of another context");
+        c->h_fused[k].P = host_plans[k]->view;
+        c->h_fused[k].coeffs = host_plans[k]->d_coeffs;
+        c->h_fused[k].sigma = host_sigma ? host_sigma[k] : 1.0;
+    }
+    CK(cudaMemcpyAsync(c->d_fused, c->h_fused, D * sizeof(FusedComp), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c->ev_fused, st));
+    FusedMapArgs a;
+    a.comps = c->d_fused; a.D = D; a.Dtot = Dtot; a.X = X; a.n = n; a.mean = mean; a.sd = sd; a.logt = log_target;
+    a.mode = mode; a.Z = Z; a.out = out;
+    cudaError_t e = ttm_launch_map_fused(a, st);
+    if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_map_fused: too many columns for one shared-memory tile");
+    CK(e);
     return TTM_OK;
 }
 

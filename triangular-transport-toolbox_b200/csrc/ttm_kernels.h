@@ -66,6 +66,26 @@ cudaError_t ttm_launch_density_acc(double* acc, const double* S, const double* d
                                    cudaStream_t st);
 cudaError_t ttm_launch_density_finish(const double* acc, const double* logt, double* out, int64_t N, cudaStream_t st);
 
+// all components of a small separable map in one launch (ttm_sep.cu: K-map-fused / K-pullback)
+struct FusedComp {
+    PlanView P;
+    const double* coeffs;  // device [m_non + m_mon]
+    double sigma;          // X_std entry dividing d_k S_k in the densities
+};
+struct FusedMapArgs {
+    const FusedComp* comps;  // device [D]
+    int D, Dtot;
+    const double* X;         // device row-major (n, Dtot) UNstandardised samples
+    int64_t n;
+    const double* mean;      // device [Dtot] or NULL (no standardisation)
+    const double* sd;
+    const double* logt;      // device [n] or NULL (mode 1)
+    int mode;                // 0 pullback density (+ Z if given), 1 pushforward density, 2 map only
+    double* Z;               // device row-major (n, D) or NULL
+    double* out;             // device [n] (modes 0, 1)
+};
+cudaError_t ttm_launch_map_fused(const FusedMapArgs& a, cudaStream_t st);
+
 // Gram matrix of [Psi_non | Psi_mon] (reference: worker_task_monotone :2966-2975, :3031-3050)
 cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch,
                             int64_t scratch_doubles, int sm_count, cudaStream_t st);

@@ -103,17 +103,6 @@ struct Slots {
     static constexpr bool NEED_P3 = has(3, 0) || has(3, 1);
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// rows of dense group g of this warp's lane -> L2 (no registers, no scoreboard): issued two groups ahead of use
-template <bool FULL>
-__device__ __forceinline__ void prefetch_group(const double* __restrict__ Xt, int64_t ld, int64_t i0, int nv, int col) {
-    const double* p = Xt + (int64_t)col * ld + i0;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-        if (FULL || r < nv) prefetch_l2(p + 32 * r);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // phase 2: sweep over the dense groups owned by this warp.  VAL: S_non partial sums -> s_Spart[warp][sample];
 // GRD: per-lane gradient sums, weights from s_W[sample].  FULL: the whole tile lies below N (no predicates).
@@ -151,7 +140,6 @@ __device__ __forceinline__ void sweep_tile(const double* __restrict__ Xt, int64_
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) xn[r] = (FULL || r < nv) ? __ldcs(p + 32 * r) : 0.0;
         }
-        if (g + 3 * NWARP < ndense) prefetch_group<FULL>(Xt, ld, i0, nv, s_col[g + 3 * NWARP]);
         const double* c = s_prod + 8 * g;
         double cf[8];
         if (VAL) {
@@ -305,14 +293,6 @@ __global__ void __launch_bounds__(TB, 2) objgrad_tile_kernel(const __grid_consta
         const int64_t base = tile * TB;
         const int64_t i = base + tid;
         const bool valid = i < N;
-        // first three groups of this warp's sweep -> L2 while the node loop runs
-        {
-            const int64_t left = (N - (base + lane) + 31) / 32;
-            const int nv = (int)(left < 0 ? 0 : (left > ROWS ? ROWS : left));
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-                if (warp + d * NWARP < ndense) prefetch_group<false>(Xt, ld, base + lane, nv, s_col[warp + d * NWARP]);
-        }
         // ---------------- phase 1: node loop ----------------
         {
             const double xc = valid ? xc_col[i] : 0.0;

@@ -183,3 +183,71 @@ cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, i
     sepobj_kernel<<<(unsigned)grid, T_SEP, smem, st>>>(P, Xt, ld, N, b, delta, partials, counter, out);
     return cudaGetLastError();
 }
+
+// -------------------------------------------------------------------------------------------------
+// K-map-fused / K-pullback (small separable maps): ALL components of the map on a tile of samples in one launch,
+// reading the caller's row-major samples directly (standardisation on the fly) and writing row-major Z and/or the
+// density -- no transposes, no per-component launches, no S / dS / accumulator round trips through HBM.
+//   map                 tm.py:2391-2437 (separable arm of s, :2550-2558)
+//   pullback density    tm.py:2646-2712:  exp( sum_k [-S_k^2/2 - log(2 pi)/2] + sum_k log(dS_k / sigma_k) )
+//   pushforward density tm.py:2618-2644:  exp( log_target - sum_k log(dS_k / sigma_k) )
+// dS_k = der_Psi_mon . coeffs_mon is evaluated on the UNstandardised samples like the reference does (:2627, :2695).
+// HBM traffic: 8 n Dtot in, 8 n (D | 1) out.  The per-term work goes through the generic factor evaluator, so the
+// host uses this kernel for maps with a few hundred terms in total (Example 05 / 06 shapes) and the per-component
+// kernels with their dense sweeps for the large ones.
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int T_FUSE = 128;
+
+__global__ void __launch_bounds__(T_FUSE) map_fused_kernel(const FusedMapArgs a) {
+    extern __shared__ double sm[];
+    const int ldt = T_FUSE + 1;
+    double* t_std = sm;                         // [Dtot][129] standardised samples of the tile, column-major
+    double* t_raw = sm + a.Dtot * ldt;          // [Dtot][129] raw samples
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * T_FUSE;
+    const int rows = (int)min((int64_t)T_FUSE, a.n - base);
+    for (int e = tid; e < rows * a.Dtot; e += T_FUSE) {
+        const int r = e / a.Dtot, v = e - r * a.Dtot;
+        const double x = a.X[(base + r) * a.Dtot + v];
+        t_raw[v * ldt + r] = x;
+        t_std[v * ldt + r] = a.mean ? (x - a.mean[v]) / a.sd[v] : x;
+    }
+    __syncthreads();
+    if (tid >= rows) return;
+    double acc = 0.0;
+    for (int k = 0; k < a.D; ++k) {
+        const PlanView P = a.comps[k].P;
+        const double* coef = a.comps[k].coeffs;
+        const double* bcoef = coef + P.m_non;
+        if (a.mode != 1) {
+            double S = 0.0;
+            for (int j = 0; j < P.m_non; ++j) S = fma(coef[j], plan_term(P, P.o_non_ptr, P.o_non_fac, j, t_std, ldt, tid), S);
+            for (int j = 0; j < P.m_mon; ++j) S = fma(bcoef[j], plan_term(P, P.o_mon_ptr, P.o_mon_fac, j, t_std, ldt, tid), S);
+            if (a.Z) a.Z[(base + tid) * a.D + k] = S;
+            acc += -0.5 * S * S - 0.91893853320467274178;
+        }
+        if (a.mode != 2) {
+            double dS = 0.0;
+            for (int j = 0; j < P.m_dmon; ++j) dS = fma(bcoef[j], plan_term(P, P.o_dmon_ptr, P.o_dmon_fac, j, t_raw, ldt, tid), dS);
+            const double ld = log(dS / a.comps[k].sigma);
+            acc += (a.mode == 0) ? ld : -ld;
+        }
+    }
+    if (a.mode != 2) a.out[base + tid] = exp(acc + ((a.mode == 1 && a.logt) ? a.logt[base + tid] : 0.0));
+}
+
+}  // namespace
+
+cudaError_t ttm_launch_map_fused(const FusedMapArgs& a, cudaStream_t st) {
+    if (a.n == 0) return cudaSuccess;
+    const size_t smem = sizeof(double) * (size_t)(2 * a.Dtot * (T_FUSE + 1));
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(map_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    map_fused_kernel<<<(unsigned)((a.n + T_FUSE - 1) / T_FUSE), T_FUSE, smem, st>>>(a);
+    return cudaGetLastError();
+}

@@ -192,6 +192,8 @@ class transport_map():
         self.D = len(monotone)
         self.skip_dimensions = X.shape[-1] - self.D
         self._plans = None
+        self._fit_info = {}
+        self.chronicle = None       # set to persistence.Chronicle() to log every fit (tm.py:4647-4660 layout)
         self._load_samples(X)
 
         # ---- term tables (replaces function_constructor_alternative, tm.py:358)
@@ -541,8 +543,38 @@ class transport_map():
         self._s_device(k, Xt, n, out)
         return self._download(out)
 
+    # ------------------------------------------------------------------ fused small-map path (K-map-fused)
+    def _fused_small(self):
+        """True when the whole map goes through ttm_map_fused (all components in one launch on row-major samples):
+        separable maps with a few hundred terms in total (Example 05 / 06 shapes).  TTM_MAP_FUSED=0 disables it."""
+        if self.monotonicity != "separable monotonicity" or not self.standardize_samples:
+            return False
+        if os.environ.get('TTM_MAP_FUSED', '1') == '0':
+            return False
+        return self._Dtot <= 64 and sum(p.m_non + p.m_mon + p.m_dmon for p in self._host_plans) <= 512
+
+    def _map_fused(self, X, mode, sigma=None, log_target=None, want_Z=False):
+        """mode 0: pullback density (and Z), 1: pushforward density, 2: Z only; X row-major (n, Dtot) host array."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        n = X.shape[0]
+        for k in range(self.D):
+            self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+        Xd = self._upload(X)
+        Z = self._empty(n, self.D) if (want_Z or mode == 2) else None
+        out = self._empty(n) if mode != 2 else None
+        lt = self._upload(log_target) if log_target is not None else None
+        plans = (B.c_void_p * self.D)(*[h.value for h in self._plans])
+        sg = np.ascontiguousarray(sigma, dtype=np.float64) if sigma is not None else None
+        ptr = lambda t: B.c_void_p(t.data_ptr()) if t is not None else None
+        B.check(self._lib.ttm_map_fused(self._ctx, plans, self.D, B.dptr(sg) if sg is not None else None, ptr(Xd), n,
+                                        self._Dtot, ptr(self._mean_d), ptr(self._std_d), ptr(lt), mode, ptr(Z), ptr(out),
+                                        self._stream()))
+        return (self._download(Z) if Z is not None else None), (self._download(out) if out is not None else None)
+
     def map(self, X=None):
         """Forward map target -> reference (tm.py:2391-2437)."""
+        if X is not None and self._fused_small():
+            return self._map_fused(X, 2)[0]
         if X is not None and self.standardize_samples:
             X = np.asarray(X, dtype=np.float64)
             Xt, n = self._to_colmajor(X, self._mean_d, self._std_d), X.shape[0]
@@ -674,6 +706,8 @@ class transport_map():
         opt = minimize(method='BFGS', fun=self.objective_function, jac=self.objective_function_jacobian,
                        x0=x0, args=(k, div))
         self._last_opt = opt
+        self._fit_info[k] = {'nit': int(opt.nit), 'nfev': int(opt.nfev), 'fun': float(opt.fun),
+                             'success': bool(opt.success)}
         return (opt.x[:div].copy(), opt.x[div:].copy())
 
     def _gram(self, k):
@@ -750,6 +784,8 @@ class transport_map():
         opt = minimize(fun=lambda b, A, k: self._sep_objective(b, A, k), method='L-BFGS-B',
                        x0=copy.copy(self.coeffs_mon[k]), jac=True, bounds=bounds, args=(A, k))
         self._last_opt = opt
+        self._fit_info[k] = {'nit': int(opt.nit), 'nfev': int(opt.nfev), 'fun': float(opt.fun),
+                             'success': bool(opt.success)}
         return (back(opt.x), opt.x)
 
     def optimize(self, K=None):
@@ -805,6 +841,20 @@ class transport_map():
         for k in K:
             self.coeffs_nonmon[k] = copy.deepcopy(results[k][0])
             self.coeffs_mon[k] = copy.deepcopy(results[k][1])
+        if self.chronicle is not None:             # fit log (persistence.Chronicle), components fitted by this rank
+            for k in mine:
+                self.chronicle.record(self, k, **self._fit_info.get(k, {}))
+
+    # ================================================================== persistence (examples' pickle format)
+    def save_coefficients(self, path):
+        """pickle {'coeffs_mon': [...], 'coeffs_nonmon': [...]} exactly as example_01.py:215-224 does."""
+        from .persistence import save_coefficients
+        save_coefficients(self, path)
+
+    def load_coefficients(self, path):
+        """Impose pickled coefficients (the reference examples' files load unchanged), example_01.py:226-231."""
+        from .persistence import load_coefficients
+        return load_coefficients(self, path)
 
     # ================================================================== inverse map
     def inverse_map(self, Z, X_star=None):
@@ -1069,6 +1119,8 @@ class transport_map():
         X = np.asarray(X, dtype=np.float64)
         if X_star is not None:
             X = np.column_stack((X_star, X))
+        if self._fused_small():
+            return self._map_fused(X, 0, sigma=[float(self.X_std[k]) for k in range(self.D)])[1]   # X_std[k], tm.py:2706
         n = X.shape[0]
         torch = self._torch
         if self.standardize_samples:
@@ -1094,6 +1146,9 @@ class transport_map():
         log_target = np.ascontiguousarray(log_target_pdf(X), dtype=np.float64)
         if X_star is not None:
             X = np.column_stack((X_star, X))
+        if self._fused_small():
+            return self._map_fused(X, 1, sigma=[float(self.X_std[k + self.skip_dimensions]) for k in range(self.D)],
+                                   log_target=log_target)[1]                          # X_std[k+skip], tm.py:2638
         n = X.shape[0]
         torch = self._torch
         Xraw_t = self._to_colmajor(X)
