@@ -318,6 +318,139 @@ def inverse_cpu_port(tm, mon, non, Dm, E, ntrain=2000, n_table=2000):
                        'samples): %d conditional samples, table root finder, single process' % (ntrain, n_table)}, parity)
 
 
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configurations: C1 Example 01, C2 Example 05 densities at 1M points,
+# C3 Example 06 EnTF cycle -- small-N / latency figures with their own parity checks, rank 0 only
+# ------------------------------------------------------------------------------------------------
+def extras(torch, with_cpu=True):
+    from cases import ex01_terms, ex05_terms, ex06_terms, ex06_cycle_inputs
+    from transport_map import transport_map
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    out = {}
+
+    def wall(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t)
+        return float(np.median(ts)), r
+
+    # ---- C1: Example 01 (spiral, N = 1e4, order-10 map, Q = 25) with the coefficients shipped with the reference
+    try:
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ex01_known_answer.npz'))
+        mon, non = ex01_terms(10)
+        tm = transport_map(X=g['X'].copy(), monotone=mon, nonmonotone=non, monotonicity='integrated rectifier',
+                           quadrature_input={'order': 25}, verbose=False)
+        rec = {'N': int(g['X'].shape[0])}
+        for k in range(2):
+            c, div = g['full_coeffs_%d' % k], int(g['full_div_%d' % k])
+            state = {'i': 0}
+
+            def ev():
+                state['i'] += 1
+                cc = c + 1e-9 * state['i']                     # a new point every call: nothing memoised
+                return tm.objective_function(cc, k, div), tm.objective_function_jacobian(cc, k, div)
+            t, _ = wall(ev, reps=9)
+            J = tm.objective_function(c, k, div)
+            rec['eval_ms_k%d' % k] = t * 1e3
+            rec['J_%d' % k] = J
+            rec['J_%d_abs_err_vs_reference' % k] = abs(J - float(g['full_J_%d' % k]))
+            rec['grad_%d_max_abs_err_vs_reference' % k] = float(np.max(np.abs(
+                tm.objective_function_jacobian(c, k, div) - g['full_grad_%d' % k])))
+        out['C1_example01'] = rec
+        del tm
+    except Exception as e:                                      # noqa: BLE001
+        out['C1_example01'] = {'error': repr(e)}
+
+    # ---- C2: Example 05 map trained on 1e3 samples, densities on 1e6 points (K-pullback / K-logdet)
+    mon, non = ex05_terms()
+    X5 = synthetic_samples(1000, 2, seed=5) * np.array([2.0, 0.5]) + np.array([1.0, -3.0])
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='separable monotonicity', verbose=False)
+    tm = transport_map(X=X5.copy(), **kw)
+    tm.optimize()
+    n = 1_000_000
+    pts = np.random.default_rng(0).uniform(-3, 3, (n, 2)) * np.array([2.0, 0.5]) + np.array([1.0, -3.0])
+    logg = lambda x: -0.5 * np.sum(x ** 2, axis=1) - np.log(2 * np.pi)
+    t_pull, dens = wall(lambda: tm.evaluate_pullback_density(pts), reps=3)
+    Zr = np.random.default_rng(1).standard_normal((n, 2))
+    t_push, dpush = wall(lambda: tm.evaluate_pushforward_density(Zr, logg), reps=3)
+    # device time of the fused kernel alone (inputs resident)
+    Xd = tm._upload(pts)
+    outd = tm._empty(n)
+    from ttt_b200 import binding as B
+    plans = (B.c_void_p * tm.D)(*[h.value for h in tm._plans])
+    sg = np.ascontiguousarray([float(tm.X_std[k]) for k in range(tm.D)])
+    ts = []
+    for rep in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        B.check(tm._lib.ttm_map_fused(tm._ctx, plans, tm.D, B.dptr(sg), B.c_void_p(Xd.data_ptr()), n, 2,
+                                      B.c_void_p(tm._mean_d.data_ptr()), B.c_void_p(tm._std_d.data_ptr()), None, 0, None,
+                                      B.c_void_p(outd.data_ptr()), tm._stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    t_dev = float(np.median(ts[1:]))
+    alg = 8 * n * (2 + 1)
+    hbm = 6534.1
+    try:
+        hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+    except Exception:
+        pass
+    rec = {'points': n, 'pullback_e2e_s': t_pull, 'pullback_points_per_s_e2e': n / t_pull,
+           'pushforward_e2e_s': t_push, 'pushforward_points_per_s_e2e': n / t_push,
+           'pullback_device_s': t_dev,
+           'roofline': {'bound': 'hbm', 'achieved': alg / t_dev / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                        'frac': alg / t_dev / 1e9 / hbm, 'algorithmic_bytes': alg,
+                        'how': 'K-pullback (ttm_map_fused, mode 0): 8 n (Dtot + 1) bytes / CUDA-event time, inputs resident'}}
+    if with_cpu:
+        from ttm_oracle import OracleMap
+        om = OracleMap(X=X5.copy(), **{k: v for k, v in kw.items() if k != 'verbose'})
+        for k in range(2):
+            om.coeffs_mon[k], om.coeffs_nonmon[k] = tm.coeffs_mon[k].copy(), tm.coeffs_nonmon[k].copy()
+        t = time.perf_counter()
+        do = om.evaluate_pullback_density(pts[:10000].copy())
+        rec['cpu_oracle_pullback_points_per_s'] = 10000 / (time.perf_counter() - t)
+        rec['pullback_max_rel_err_vs_oracle'] = float(np.max(np.abs(dens[:10000] - do) / np.maximum(1e-300, np.abs(do))))
+        dpo = om.evaluate_pushforward_density(Zr[:2000].copy(), logg)
+        rec['pushforward_max_rel_err_vs_oracle'] = float(np.max(np.abs(dpush[:2000] - dpo) / np.maximum(1e-300, np.abs(dpo))))
+    out['C2_example05_densities'] = rec
+    del tm, Xd, outd
+
+    # ---- C3: one EnTF cycle of Example 06 (reset -> optimize -> map -> inverse_map), separable + L2
+    mon, non = ex06_terms(3)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='separable monotonicity', regularization='l2',
+              regularization_lambda=0.05, verbose=False)
+    cyc_out = []
+    for N in (500, 1000, 10000):
+        dummy, cyc = ex06_cycle_inputs(N)
+        tm = transport_map(X=dummy.copy(), **kw)
+
+        def cycle(m):
+            m.reset(cyc.copy())
+            m.optimize()
+            Z = m.map(cyc.copy())
+            return m.inverse_map(X_star=np.full((N, 1), 1.5), Z=Z)
+        t, post = wall(lambda: cycle(tm), reps=7)
+        rec = {'N': N, 'gpu_cycle_ms': t * 1e3, 'posterior_mean': post.mean(axis=0).tolist()}
+        if with_cpu:
+            from ttm_oracle import OracleMap
+            om = OracleMap(X=dummy.copy(), **{k: v for k, v in kw.items() if k != 'verbose'})
+            cycle(om)
+            t0 = time.perf_counter()
+            po = cycle(om)
+            rec['cpu_oracle_cycle_ms'] = (time.perf_counter() - t0) * 1e3
+            rec['max_abs_diff_vs_oracle'] = float(np.max(np.abs(po - post)))
+        cyc_out.append(rec)
+        del tm
+    out['C3_example06_entf_cycle'] = cyc_out
+    return out
+
+
 def multi_gpu_check(rank, world, dist, torch):
     """Sample-sharded evaluation (the K < #GPUs path of SURVEY 8(e): every rank holds N/world rows, (J, grad) are
     all-reduced) against the same evaluation on the whole ensemble held by one rank (the component-sharded layout)."""
@@ -524,6 +657,12 @@ def run_gpu(args):
         del tm, flush
         torch.cuda.empty_cache()
         inv = inverse_metric(rank, world, dist, torch, with_cpu=not args.no_cpu)
+    ext = None
+    if not args.no_extras and rank == 0 and world == 1:
+        try:
+            ext = extras(torch, with_cpu=not args.no_cpu)
+        except Exception as e:                                  # noqa: BLE001  (extras never take the headline down)
+            ext = {'error': repr(e)}
 
     if rank == 0:
         value = D * args.steps / t_max
@@ -630,6 +769,8 @@ def run_gpu(args):
                 'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                 'sample': 'components k=0,31,63 of the same C4 map on %d samples (single process, BLAS threads = %s), '
                           'evals/s scaled linearly to N=1M; host has %d cores' % (n_cpu, os.environ.get('OPENBLAS_NUM_THREADS'), cores)}
+        if ext is not None:
+            line['other_configs'] = ext
         if inv is not None:
             line['inverse_map'] = inv
             if 'parity_max_abs' in inv:
@@ -651,6 +792,7 @@ def main():
     ap.add_argument('--n', type=int, default=N_FULL, help='samples (default: the metric point, 1M)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-inverse', action='store_true', help='skip the secondary inverse_map metric (config C5)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the C1/C2/C3 small-configuration figures')
     ap.add_argument('--no-fit', action='store_true', help='skip the end-to-end optimize() of the C4 map')
     ap.add_argument('--streams', type=int, default=2, help='CUDA streams the evaluations of a step are issued on')
     ap.add_argument('--bps', type=int, default=2, help='resident blocks per SM of one launch (x streams = blocks per SM)')

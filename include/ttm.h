@@ -150,6 +150,12 @@ int ttm_map_fused(ttm_ctx* ctx, ttm_plan* const* host_plans, int D, const double
  * (M, M), M = m_non + m_mon.  scratch: as many (M8*M8) blocks as fit are used for split-N partials. */
 int ttm_gram(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch,
              int64_t scratch_doubles, void* stream);
+/* the same, but only the entries G[i][j] with max(i, j) >= 64*(first_col/64) are computed (the others are set to 0):
+ * Psi^T [Psi_mon] and the neighbouring tiles.  When the components of a map share their nonmonotone basis (the term
+ * list of one is a prefix of another's), the leading block Psi_non^T Psi_non and its Cholesky factor come from ONE
+ * full Gram of the longest list, and every component only needs this tail. */
+int ttm_gram_tail(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, int first_col, double* G, double* scratch,
+                  int64_t scratch_doubles, void* stream);
 
 /* ---- K-sepobj ---------------------------------------------------------------------------------
  * replaces: the sample-dependent part of fun_mon_objective, tm.py:2990-3006.

@@ -226,6 +226,35 @@ def headline_sep_coeffs(mon, non):
     return cm, cn
 
 
+def adapt_separable_case():
+    """Seeded input of the separable structure search (adapt_map, tm.py:373-657): a 3-D ensemble with one skewed
+    marginal and one nonlinear dependence."""
+    rng = np.random.default_rng(31)
+    n = 400
+    x0 = rng.standard_normal(n)
+    x1 = np.exp(0.5 * rng.standard_normal(n)) + 0.2 * x0
+    x2 = 0.7 * x0 ** 2 + 0.5 * rng.standard_normal(n)
+    X = np.column_stack((x0, x1, x2))
+    kw = dict(monotone=None, nonmonotone=None, monotonicity='separable monotonicity', adaptation=True,
+              adaptation_map_type='separable', verbose=False)
+    call = dict(maxorder_mon=4, maxorder_nonmon=3, threshold_sw=0.1, threshold_prec=0.1)
+    return X, kw, call
+
+
+def adapt_cross_case():
+    """Seeded input of the cross-term structure search (adaptation_cross_terms, tm.py:4575-4950)."""
+    rng = np.random.default_rng(32)
+    n = 300
+    x0 = rng.standard_normal(n)
+    x1 = 0.6 * x0 ** 2 + 0.6 * rng.standard_normal(n)
+    X = np.column_stack((x0, x1))
+    kw = dict(monotone=None, nonmonotone=None, monotonicity='integrated rectifier', adaptation=True,
+              adaptation_map_type='cross-terms', adaptation_max_order=3, adaptation_max_iterations=3,
+              quadrature_input={'order': 15}, verbose=False)
+    call = dict(increment=1e-6, chronicle=False)
+    return X, kw, call
+
+
 def fresh_kwargs(case):
     """Deep copy of the constructor kwargs (the reference mutates quadrature_input, tm.py:224)."""
     return copy.deepcopy(case['kwargs'])

@@ -50,3 +50,42 @@ def test_bad_options_raise_like_the_reference():
         parse_entry('XBF 0', np.zeros(2, dtype=int), 0, True, None)
     with pytest.raises(Exception, match="'LIN' modifier"):
         parse_entry([0, 'LIN'], np.zeros(2, dtype=int), 0, True, None)
+
+
+@pytest.mark.parametrize('name', [n for n in sorted(CASES) if any(
+    type(e) == str for k in range(len(CASES[n]['kwargs']['monotone']))
+    for e in CASES[n]['kwargs']['monotone'][k] + CASES[n]['kwargs']['nonmonotone'][k])])
+def test_refresh_special_equals_rebuild_and_tables_do_not_depend_on_the_data(name):
+    """reset() moves the special-term centres / scales (tm.py:800): patching them into the double blob must equal a
+    full recompilation, and the int blob (factor table, term lists) must not change -- also when centres COINCIDE
+    (tied quantiles of a discrete column, ST_scale_mode='static'), which used to merge factors."""
+    import copy
+    case = CASES[name]
+    kw = fresh_kwargs(case)
+    om = OracleMap(X=case['X'].copy(), **kw)
+    fam, polyfunc, polyder, _ = resolve_family(kw.get('polynomial_type', 'hermite function'))
+    Dtot = case['X'].shape[1]
+    rng = np.random.default_rng(0)
+    for k in range(om.D):
+        c = k + om.skip_dimensions
+        args = (k, c, Dtot, fam, polyfunc, polyder, kw['monotone'][k], kw['nonmonotone'][k])
+        plan = ComponentPlan(*args, om.special_terms, kw.get('linearization'))
+        for variant in ('moved', 'tied'):
+            st = copy.deepcopy(om.special_terms)
+
+            def perturb(d):
+                for key, v in d.items():
+                    if key == 'cross-terms':
+                        perturb(v)
+                    elif len(v['centers']):
+                        if variant == 'moved':
+                            v['centers'] = v['centers'] + rng.standard_normal(len(v['centers'])) * 0.1
+                            v['scales'] = v['scales'] * (1.0 + 0.1 * rng.random(len(v['scales'])))
+                        else:
+                            v['centers'] = np.zeros_like(v['centers'])
+                            v['scales'] = np.ones_like(v['scales'])
+            perturb(st[c])
+            fresh = ComponentPlan(*args, st, kw.get('linearization'))
+            assert np.array_equal(fresh.iblob, plan.iblob), (name, k, variant)
+            plan.refresh_special(st)
+            assert np.array_equal(plan.dblob, fresh.dblob), (name, k, variant)

@@ -60,6 +60,7 @@ def lib():
             'ttm_map_fused': [c_void_p, ctypes.POINTER(c_void_p), c_int, _dp, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                               c_void_p, c_int, c_void_p, c_void_p, c_void_p],
             'ttm_gram': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p],
+            'ttm_gram_tail': [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p],
             'ttm_sep_objgrad': [c_void_p, c_void_p, c_int64, c_int64, _dp, _dp, c_void_p],
             'ttm_mon_table': [c_void_p, c_int, c_void_p, c_void_p],
             'ttm_inverse_table': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p],

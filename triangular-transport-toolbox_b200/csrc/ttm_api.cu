@@ -431,9 +431,15 @@ int ttm_map_fused(ttm_ctx* c, ttm_plan* const* host_plans, int D, const double* 
 
 int ttm_gram(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch, int64_t scratch_doubles,
              void* stream) {
-    if (!p || !Xt || !G || !scratch || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_gram: bad arguments");
+    return ttm_gram_tail(p, Xt, ld, N, 0, G, scratch, scratch_doubles, stream);
+}
+
+int ttm_gram_tail(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, int first_col, double* G, double* scratch,
+                  int64_t scratch_doubles, void* stream) {
+    if (!p || !Xt || !G || !scratch || N <= 0 || ld < N || first_col < 0 || first_col > p->m)
+        return fail(TTM_ERR_ARG, "ttm_gram: bad arguments");
     CK(cudaSetDevice(p->ctx->device));
-    cudaError_t e = ttm_launch_gram(p->view, Xt, ld, N, G, scratch, scratch_doubles, p->ctx->sm_count, (cudaStream_t)stream);
+    cudaError_t e = ttm_launch_gram(p->view, Xt, ld, N, first_col, G, scratch, scratch_doubles, p->ctx->sm_count, (cudaStream_t)stream);
     if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_gram: scratch too small or too many terms for one shared-memory tile");
     CK(e);
     return TTM_OK;

@@ -27,16 +27,17 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// blockIdx.x = tile pair (ti <= tj), blockIdx.y = row split
+// blockIdx.x = tile pair (ti <= tj, tj >= tj0), blockIdx.y = row split.  tj0 > 0: only the tile columns from tj0 on
+// (the "tail" Gram: Psi^T [last columns], all a component needs when the leading block comes from a donor).
 __global__ void __launch_bounds__(T_GRAM) syrk_dmma_kernel(const double* __restrict__ Psi, int64_t n, int Mp,
-                                                           int nsplit, int accumulate,
+                                                           int nsplit, int accumulate, int tj0,
                                                            double* __restrict__ partial) {
     __shared__ double As[GK][GLD];
     __shared__ double Bs[GK][GLD];
     const int nt = (Mp + GT - 1) / GT;
-    int ti = 0, rem = blockIdx.x;
-    while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
-    const int tj = ti + rem;
+    int tj = tj0, rem = blockIdx.x;                  // column tile tj holds the pairs ti = 0..tj
+    while (rem > tj) { rem -= tj + 1; ++tj; }
+    const int ti = rem;
     const int split = blockIdx.y;
     const int64_t rows_per = ((n + nsplit - 1) / nsplit + GK - 1) / GK * GK;
     const int64_t r_lo = (int64_t)split * rows_per;
@@ -93,11 +94,12 @@ __global__ void __launch_bounds__(T_GRAM) syrk_dmma_kernel(const double* __restr
 }
 
 // G[i][j] = sum over splits (fixed order) of the stored element: element (r, c) of the upper block triangle
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nsplit, int Mp, int M,
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nsplit, int Mp, int M, int tj0,
                                    double* __restrict__ G) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M * M) return;
     const int i = e / M, j = e % M;
+    if (max(i, j) / GT < tj0) { G[e] = 0.0; return; }   // tail Gram: the leading block is not computed
     // tile (i/64, j/64) is stored if its row tile <= column tile; otherwise use the transposed element
     const int r = (i / GT <= j / GT) ? i : j, c = (i / GT <= j / GT) ? j : i;
     double s = 0.0;
@@ -107,13 +109,14 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nspli
 
 }  // namespace
 
-cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch,
-                            int64_t scratch_doubles, int sm_count, cudaStream_t st) {
+cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int64_t N, int first_col, double* G,
+                            double* scratch, int64_t scratch_doubles, int sm_count, cudaStream_t st) {
     const int M = P.m_non + P.m_mon;
     if (M == 0 || N == 0) return cudaSuccess;
     const int Mp = (M + 7) / 8 * 8;
     const int nt = (Mp + GT - 1) / GT;
-    const int npairs = nt * (nt + 1) / 2;
+    const int tj0 = first_col / GT;                  // entries (i, j) with max(i, j) >= tj0 * 64 are computed
+    const int npairs = nt * (nt + 1) / 2 - tj0 * (tj0 + 1) / 2;
     int nsplit = (2 * sm_count + npairs - 1) / npairs;
     if (nsplit > 64) nsplit = 64;
     if ((int64_t)nsplit * GK > N) nsplit = (int)((N + GK - 1) / GK);
@@ -132,8 +135,8 @@ cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int
         e = ttm_launch_basis_concat(P, Xt + n0, ld, n, Psi, Mp, st);
         if (e != cudaSuccess) return e;
         dim3 grid((unsigned)npairs, (unsigned)nsplit);
-        syrk_dmma_kernel<<<grid, T_GRAM, 0, st>>>(Psi, n, Mp, nsplit, it > 0 ? 1 : 0, partial);
+        syrk_dmma_kernel<<<grid, T_GRAM, 0, st>>>(Psi, n, Mp, nsplit, it > 0 ? 1 : 0, tj0, partial);
     }
-    gram_reduce_kernel<<<(M * M + 255) / 256, 256, 0, st>>>(partial, nsplit, Mp, M, G);
+    gram_reduce_kernel<<<(M * M + 255) / 256, 256, 0, st>>>(partial, nsplit, Mp, M, tj0, G);
     return cudaGetLastError();
 }

@@ -87,8 +87,8 @@ struct FusedMapArgs {
 cudaError_t ttm_launch_map_fused(const FusedMapArgs& a, cudaStream_t st);
 
 // Gram matrix of [Psi_non | Psi_mon] (reference: worker_task_monotone :2966-2975, :3031-3050)
-cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int64_t N, double* G, double* scratch,
-                            int64_t scratch_doubles, int sm_count, cudaStream_t st);
+cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int64_t N, int first_col, double* G,
+                            double* scratch, int64_t scratch_doubles, int sm_count, cudaStream_t st);
 
 // reduced separable objective: sum log dS, colsum(dPsi/dS) (reference: fun_mon_objective :2978-3018)
 cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* b,

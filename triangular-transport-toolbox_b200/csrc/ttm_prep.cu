@@ -122,6 +122,68 @@ __global__ void __launch_bounds__(T_BAS) basis_kernel(const PlanView P, int o_pt
     }
 }
 
+// K-basis, dense form (nonmonotone basis of a component whose terms are constants + per-variable polynomial /
+// Hermite-function terms): one column load, one Gaussian weight and one recurrence ladder per (sample, variable)
+// shared by all orders of that variable, instead of one generic factor evaluation (with its own exp) per term.
+// Terms are visited in coefficient order and the last column's x, e^{-x^2/4} and ladder are cached, so the usual
+// term order (all terms of a variable adjacent) costs one exp per variable.  Psi rows leave through a shared-memory
+// transpose tile in 128-byte pieces.  HBM-bound when writing: 8 N (k+1) read + 8 N m written.
+constexpr int BD_MAXORD = 1 << 20;   // no limit: the ladder is a two-term state
+
+__global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
+                                                            int64_t N, double* __restrict__ Psi, int64_t ldp, int coff) {
+    __shared__ double tile[TJ_BAS][T_BAS + 1];
+    extern __shared__ int s_t2e[];               // term -> dense entry (group * stride + slot), -1: constant
+    const int m = P.m_non;
+    const int stride = 2 * (P.dense_maxord + 1);
+    for (int j = threadIdx.x; j < m; j += T_BAS) s_t2e[j] = -1;
+    __syncthreads();
+    for (int e = threadIdx.x; e < P.ndense * stride; e += T_BAS) {
+        const int j = P.ib[P.o_dense_idx + e];
+        if (j >= 0) s_t2e[j] = e;
+    }
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * T_BAS;
+    const int64_t i = base + threadIdx.x;
+    const int64_t ic = i < N ? i : N - 1;
+    int last_g = -1, cur = 0;                    // cached group; ladder state: pc = P_cur(x), pm = P_{cur-1}(x)
+    double x = 0.0, ga = 0.0, pc = 1.0, pm = 0.0;
+    bool have_ga = false;
+    for (int j0 = 0; j0 < m; j0 += TJ_BAS) {
+        const int w = min(TJ_BAS, m - j0);
+        for (int t = 0; t < w; ++t) {
+            const int e = s_t2e[j0 + t];
+            double v = 1.0;                      // constant term (np.ones, tm.py:890)
+            if (e >= 0) {
+                const int g = e / stride, slot = e - g * stride, o = slot >> 1;
+                if (g != last_g) {
+                    x = Xt[(int64_t)P.ib[P.o_dense_var + 4 * g] * ld + ic];
+                    last_g = g; cur = 0; pc = 1.0; pm = 0.0; have_ga = false;
+                }
+                if (o < cur) { cur = 0; pc = 1.0; pm = 0.0; }   // orders usually ascend within a variable
+                for (; cur < o; ++cur) {         // three-term recurrence of the family up to order o
+                    double A, B, C;
+                    rec_coef(P.family, cur, A, B, C);
+                    const double pn = fma(fma(A, x, B), pc, -C * pm);
+                    pm = pc; pc = pn;
+                }
+                v = P.db[P.o_d_dense_scale + e] * pc;
+                if (slot & 1) {
+                    if (!have_ga) { ga = exp(-0.25 * x * x); have_ga = true; }
+                    v *= ga;
+                }
+            }
+            tile[t][threadIdx.x] = v;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < w * T_BAS; e += T_BAS) {
+            const int s = e / w, t = e - s * w;
+            if (base + s < N) Psi[(base + s) * ldp + coff + j0 + t] = tile[t][s];
+        }
+        __syncthreads();
+    }
+}
+
 // 8 independent DFMA chains per thread
 __global__ void fp64_peak_kernel(double* sink, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -175,7 +237,10 @@ cudaError_t ttm_launch_basis(const PlanView& P, int which, const double* Xt, int
     else if (which == 1) { o_ptr = P.o_mon_ptr; o_fac = P.o_mon_fac; m = P.m_mon; }
     else { o_ptr = P.o_dmon_ptr; o_fac = P.o_dmon_fac; m = P.m_dmon; }
     if (m == 0 || N == 0) return cudaSuccess;
-    basis_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, 0, st>>>(P, o_ptr, o_fac, m, Xt, ld, N, Psi, m, 0);
+    if (which == 0 && P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && m * sizeof(int) <= 40 * 1024)
+        basis_dense_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, m * sizeof(int), st>>>(P, Xt, ld, N, Psi, m, 0);
+    else
+        basis_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, 0, st>>>(P, o_ptr, o_fac, m, Xt, ld, N, Psi, m, 0);
     return cudaGetLastError();
 }
 
@@ -184,8 +249,12 @@ cudaError_t ttm_launch_basis_concat(const PlanView& P, const double* Xt, int64_t
                                     int64_t ldp, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + T_BAS - 1) / T_BAS);
-    if (P.m_non > 0)
-        basis_kernel<<<grid, T_BAS, 0, st>>>(P, P.o_non_ptr, P.o_non_fac, P.m_non, Xt, ld, n, Psi, ldp, 0);
+    if (P.m_non > 0) {
+        if (P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && P.m_non * sizeof(int) <= 40 * 1024)
+            basis_dense_kernel<<<grid, T_BAS, P.m_non * sizeof(int), st>>>(P, Xt, ld, n, Psi, ldp, 0);
+        else
+            basis_kernel<<<grid, T_BAS, 0, st>>>(P, P.o_non_ptr, P.o_non_fac, P.m_non, Xt, ld, n, Psi, ldp, 0);
+    }
     if (P.m_mon > 0)
         basis_kernel<<<grid, T_BAS, 0, st>>>(P, P.o_mon_ptr, P.o_mon_fac, P.m_mon, Xt, ld, n, Psi, ldp, P.m_non);
     return cudaGetLastError();

@@ -110,6 +110,7 @@ class _Factors:
         self.index = {}
         self.ints = []
         self.dbls = []
+        self.special = {}       # factor index -> (variable, occurrence slot, cross-term flag) of a special term
 
     def add(self, var, kind, order=0, scale=1.0, scale2=0.0, mu=0.0, sigma=1.0, ident=None):
         """`ident` identifies a special term by its position (occurrence slot, cross-term flag) instead of by its
@@ -120,6 +121,8 @@ class _Factors:
             self.index[key] = len(self.ints)
             self.ints.append((int(var), int(kind), int(order), 0))
             self.dbls.append((float(scale), float(scale2), float(mu), float(sigma)))
+            if ident is not None:
+                self.special[len(self.ints) - 1] = (int(var), int(ident[0]), bool(ident[1]))
         return self.index[key]
 
 
@@ -139,6 +142,17 @@ class ComponentPlan:
         self.ub = np.full(len(self.mon_recs), np.inf)
         self.has_special = any(r['type'] == 'st' for r in self.mon_recs + self.non_recs)
         self.build(special_terms)
+
+    def refresh_special(self, special_terms):
+        """New centres / scales of the special terms into the existing double blob (the tables and the int blob do
+        not depend on them).  Equivalent to build(special_terms), at a fraction of its cost."""
+        for f, var, slot, cross, pos_fac, pos_ent in self._st_patch:
+            d = special_terms[self.c]['cross-terms'] if cross else special_terms[self.c]
+            mu, sg = float(d[var]['centers'][slot]), float(d[var]['scales'][slot])
+            self.dblob[pos_fac + 2], self.dblob[pos_fac + 3] = mu, sg
+            for pe in pos_ent:
+                self.dblob[pe + 1], self.dblob[pe + 2] = mu, sg
+        return self
 
     # ------------------------------------------------------------------ factors of one record
     def _st_params(self, rec, special_terms):
@@ -361,6 +375,17 @@ class ComponentPlan:
         self.dblob = np.ascontiguousarray(np.concatenate(db), dtype=np.float64)
         self.maxord, self.nst, self.nslot = maxord, nst, nslot
         self.dense_maxord = dense_maxord
+        # where the centres / scales of the special terms sit in the double blob: refresh_special() patches them in
+        # place when the ensemble changes (reset(), tm.py:800) instead of recompiling the tables
+        o_fac, o_ent = int(h[H_D_FAC]), int(h[H_D_ENT])
+        ent_of = {}
+        e = 0
+        for v in sorted(slow):
+            for f, _ in sorted(slow[v], key=lambda t: (0, fi[t[0], 2]) if fi[t[0], 1] <= F_POLY_HF else (1, 0)):
+                ent_of.setdefault(int(f), []).append(e)
+                e += 1
+        self._st_patch = [(f, var, slot, cross, o_fac + 4 * f, [o_ent + 4 * q for q in ent_of.get(f, [])])
+                          for f, (var, slot, cross) in F.special.items()]
         # host copies of the nonmonotone structure (the fused inverse packs its coefficient matrix from them)
         self.const_idx = list(const_idx)
         self.n_slow, self.n_multi = len(var_idx), len(multi_idx)

@@ -9,7 +9,8 @@ defaults tm.py:12-39, public attributes, `optimize`, `map`, `inverse_map`, `rese
 scipy optimizer steps (BFGS / L-BFGS-B, tm.py:3252-3257 / :3108-3114), the m x m linear algebra of
 the separable fit, quantile look-ups for special-term placement, and option/error handling.
 
-Out of scope: map adaptation (`adapt_map`), adaptive quadrature order, the
+Map adaptation (`adapt_map`, `adaptation_cross_terms`) runs on top of this path (adaptation.py).
+Out of scope: adaptive quadrature order, the
 generated-source strings (`fun_mon_strings` ...), `projectedNewton`, progress bars.
 
 PyTorch is used for device buffers, streams and (multi-GPU) torch.distributed only.
@@ -167,8 +168,6 @@ class transport_map():
         self.polyfunc_str = "np.polynomial." + self.polyfunc.__name__
 
         self.adaptation = adaptation
-        if adaptation:
-            raise NotImplementedError("map adaptation is out of scope of the CUDA path (SURVEY.md section 2)")
         self.adaptation_map_type = adaptation_map_type.lower()
         self.adaptation_max_order = adaptation_max_order
         self.adaptation_skip_dimensions = adaptation_skip_dimensions
@@ -189,8 +188,15 @@ class transport_map():
 
         # ---- samples (tm.py:311-314, 327-328)
         self.standardize_samples = standardize_samples
-        self.D = len(monotone)
-        self.skip_dimensions = X.shape[-1] - self.D
+        if not self.adaptation:
+            self.D = len(monotone)
+            self.skip_dimensions = X.shape[-1] - self.D
+        else:
+            # adaptation starts from a dummy map, one constant term per list (tm.py:331-345)
+            self.D = X.shape[-1] - self.adaptation_skip_dimensions
+            self.skip_dimensions = self.adaptation_skip_dimensions
+            self.monotone = [[[]] for _ in range(self.D)]
+            self.nonmonotone = [[[]] for _ in range(self.D)]
         self._plans = None
         self._fit_info = {}
         self.chronicle = None       # set to persistence.Chronicle() to log every fit (tm.py:4647-4660 layout)
@@ -420,20 +426,59 @@ class transport_map():
         B.check(self._lib.ttm_plan_info(h, info))
         return {'tile_ok': bool(info[0]), 'dense_mask': int(info[1]), 'n_out_terms': int(info[2])}
 
+    def function_constructor_alternative(self, k=None):
+        """Re-compile the term tables after `monotone` / `nonmonotone` were edited (tm.py:1263-1856): of the whole map
+        (k None: special terms are re-counted and re-placed, coefficients re-initialised to coeffs_init, :1300-1301,
+        :1491, :1610) or of component k only (tables only; coefficients and special-term placement untouched, as in
+        the reference's partial construction).  Used by the adaptation routines."""
+        if k is None:
+            self.check_for_special_terms()
+            self.determine_special_term_locations()
+            self._compile_plans()
+            self.coeffs_mon = [np.ones(p.m_mon) * self.coeffs_init for p in self._host_plans]
+            self.coeffs_nonmon = [np.ones(len(self.nonmonotone[kk])) * self.coeffs_init for kk in range(self.D)]
+        elif np.isscalar(k):
+            k = int(k)
+            p = ComponentPlan(k, k + self.skip_dimensions, self._Dtot, self._family, self.polyfunc, self.polyfunc_der,
+                              self.monotone[k], self.nonmonotone[k], self.special_terms, self.linearization)
+            self._host_plans[k] = p
+            self._lib.ttm_plan_destroy(self._plans[k])
+            self._plans[k] = self._create_plan(p)
+            self._plan_info[k] = self._query_plan(self._plans[k])
+            self._inv_pack_cache = {}
+        else:
+            raise Exception("'k' for function_constructor_alternative must be either None or an integer.")
+        if self.monotonicity.lower() == 'separable monotonicity':
+            self.optimization_constraints_lb = [p.lb.copy() for p in self._host_plans]
+            self.optimization_constraints_ub = [p.ub.copy() for p in self._host_plans]
+        self._make_callables()
+        self._reset_lazy()
+
+    # ================================================================== adaptation (adaptation.py)
+    def adapt_map(self, coeffs={}, maxorder_mon=10, maxorder_nonmon=10, threshold_sw=0.1, threshold_prec=0.1,
+                  sequential_updates=False, map_finished=None):
+        """tm.py:373-657."""
+        from . import adaptation
+        if self.adaptation_map_type == 'separable':
+            adaptation.adapt_separable(self, maxorder_mon, maxorder_nonmon, threshold_sw, threshold_prec, map_finished)
+        elif self.adaptation_map_type == 'cross-terms':
+            self.adaptation_cross_terms(*coeffs)
+        else:
+            raise Exception("Currently, only adaptation_map_type = 'cross-terms' is implemented.")
+
+    def adaptation_cross_terms(self, increment=1E-6, chronicle=False):
+        """tm.py:4575-4950."""
+        from . import adaptation
+        adaptation.adapt_cross_terms(self, increment, chronicle)
+
     def _refresh_special_terms(self):
-        """Special-term centres/scales moved (reset / precalculate): rebuild the double blobs.  The int blob does not
-        depend on the data (special-term factors are identified by position, plan._Factors.add); should it ever
-        differ, the plan is re-created instead of indexing stale tables."""
+        """Special-term centres/scales moved (reset / precalculate): patch them into the double blobs.  The tables and
+        the int blob do not depend on the data (special-term factors are identified by position, plan._Factors.add;
+        tests/test_plan_compiler.py checks refresh_special against a full rebuild, tied centres included)."""
         for k, p in enumerate(self._host_plans):
             if p.has_special:
-                old = p.iblob
-                p.build(self.special_terms)
-                if old.shape == p.iblob.shape and np.array_equal(old, p.iblob):
-                    B.check(self._lib.ttm_plan_update_doubles(self._plans[k], B.dptr(p.dblob), p.dblob.size))
-                else:
-                    self._lib.ttm_plan_destroy(self._plans[k])
-                    self._plans[k] = self._create_plan(p)
-                    self._plan_info[k] = self._query_plan(self._plans[k])
+                p.refresh_special(self.special_terms)          # patches centres / scales in place (== p.build(...))
+                B.check(self._lib.ttm_plan_update_doubles(self._plans[k], B.dptr(p.dblob), p.dblob.size))
 
     def _free_plans(self):
         if getattr(self, '_plans', None):
