@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,6 +65,9 @@ struct ttm_plan {
     unsigned int* d_counter = nullptr;
     double* h_pin = nullptr;       // pinned staging [2*(1+m)]
     cudaEvent_t ev_h2d = nullptr;  // recorded after every H2D copy out of h_pin: the buffer is not rewritten before it
+    double* h_res = nullptr;       // pinned + mapped [1+m] result mirror written by the kernels' last block, then
+    unsigned long long* h_flag = nullptr;   // the launch's sequence number (after a system fence)
+    unsigned long long seq = 0;
     int gram_mode = 0;
     int tile_ok = 0, dense_mask = 0, n_out_terms = 0;   // tile-kernel eligibility (parse_view)
 };
@@ -220,6 +224,9 @@ int ttm_plan_create(ttm_ctx* c, const int32_t* host_iblob, int64_t n_int, const 
     CK(cudaMemset(p->d_coeffs, 0, (p->m + 1) * sizeof(double)));
     CK(cudaMallocHost(&p->h_pin, 2 * m1 * sizeof(double)));
     CK(cudaEventCreateWithFlags(&p->ev_h2d, cudaEventDisableTiming));
+    CK(cudaHostAlloc(&p->h_res, (m1 + 2) * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+    p->h_flag = reinterpret_cast<unsigned long long*>(p->h_res + m1 + 1);
+    *p->h_flag = 0ull;
     *host_out = p;
     return TTM_OK;
 #undef CK
@@ -253,6 +260,7 @@ int ttm_plan_destroy(ttm_plan* p) {
     cudaFree(p->d_partials); cudaFree(p->d_counter);
     if (p->h_pin) cudaFreeHost(p->h_pin);
     if (p->ev_h2d) cudaEventDestroy(p->ev_h2d);
+    if (p->h_res) cudaFreeHost(p->h_res);
     delete p;
     return TTM_OK;
 }
@@ -316,6 +324,7 @@ static int fill_obj(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, ObjArg
     a.xis = c->d_xis; a.ws = c->d_ws; a.Q = c->Q; a.wsum = c->wsum;
     a.rect = c->rect; a.delta = c->delta;
     a.partials = p->d_partials; a.counter = p->d_counter; a.out = p->d_out;
+    a.out_host = p->h_res; a.flag_host = p->h_flag; a.seq = ++p->seq;
     a.S_out = nullptr;
     a.max_grid = MAX_GRID;
     a.blocks_per_sm = c->blocks_per_sm;
@@ -348,13 +357,37 @@ int ttm_plan_get_out(ttm_plan* p, double* host_out, int n, void* stream) {
     return TTM_OK;
 }
 
+// Wait for the launch with sequence number p->seq to publish its result in the mapped host mirror, then copy it out.
+// A spinning read of pinned memory replaces cudaMemcpyAsync(D2H) + cudaStreamSynchronize (~15 us per evaluation,
+// which matters for the latency-bound small-N fits); errors are picked up by polling the stream every so often.
+static int wait_result(ttm_plan* p, double* host_out, int n, cudaStream_t st) {
+    volatile unsigned long long* flag = p->h_flag;
+    const unsigned long long want = p->seq;
+    for (unsigned long long spins = 0; *flag != want; ++spins) {
+        if ((spins & 0xffff) == 0xffff) {
+            cudaError_t e = cudaStreamQuery(st);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "kernel execution");
+            if (e == cudaSuccess && *flag != want) {          // finished without publishing: should not happen
+                CK(cudaMemcpy(host_out, p->d_out, n * sizeof(double), cudaMemcpyDeviceToHost));
+                return TTM_OK;
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    std::memcpy(host_out, p->h_res, n * sizeof(double));
+    return TTM_OK;
+}
+
 int ttm_objgrad_ir(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* host_coeffs, double* host_out,
                    void* stream) {
     int rc = ttm_plan_set_coeffs(p, host_coeffs, stream);
     if (rc) return rc;
     rc = ttm_objgrad_ir_launch(p, Xt, ld, N, stream);
     if (rc) return rc;
-    return ttm_plan_get_out(p, host_out, 1 + p->m, stream);
+    return wait_result(p, host_out, 1 + p->m, (cudaStream_t)stream);
 }
 
 int ttm_eval_s_ir(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, double* S_out, void* stream) {
@@ -451,16 +484,19 @@ int ttm_sep_objgrad(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const 
     CK(cudaSetDevice(p->ctx->device));
     const int mm = p->view.m_dmon;
     if (mm > p->m) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: inconsistent plan");
+    // the coefficients are read by the kernel straight from pinned (mapped) host memory and the result comes back
+    // the same way: one launch, no copies, no stream synchronisation (the call returns after the result arrived, so
+    // h_pin is free again)
     CK(cudaEventSynchronize(p->ev_h2d));
     std::memcpy(p->h_pin, host_b, mm * sizeof(double));
     double* d_b = p->d_coeffs + p->view.m_non;
-    CK(cudaMemcpyAsync(d_b, p->h_pin, mm * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    CK(cudaEventRecord(p->ev_h2d, (cudaStream_t)stream));
-    cudaError_t e = ttm_launch_sepobj(p->view, Xt, ld, N, d_b, p->ctx->delta, p->d_partials, p->d_counter, p->d_out,
-                                      MAX_GRID, p->ctx->sm_count, (cudaStream_t)stream);
+    p->seq += 1;
+    cudaError_t e = ttm_launch_sepobj(p->view, Xt, ld, N, p->h_pin, d_b, p->ctx->delta, p->d_partials, p->d_counter,
+                                      p->d_out, p->h_res, p->h_flag, p->seq, MAX_GRID, p->ctx->sm_count,
+                                      (cudaStream_t)stream);
     if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_sep_objgrad: too many monotone terms for shared memory");
     CK(e);
-    return ttm_plan_get_out(p, host_out, 1 + mm, stream);
+    return wait_result(p, host_out, 1 + mm, (cudaStream_t)stream);
 }
 
 int ttm_mon_table(ttm_plan* p, int ntab, double* table, void* stream) {

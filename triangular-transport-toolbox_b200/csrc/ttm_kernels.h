@@ -20,6 +20,9 @@ struct ObjArgs {
     double* partials;      // device [max_grid][1+m]
     unsigned int* counter; // device, zero on entry, zero on exit
     double* out;           // device [1+m]: J, grad
+    double* out_host;      // pinned host mirror of `out` (mapped): written by the last block together with `out`,
+    unsigned long long* flag_host;   // followed by a system fence and the sequence number of the launch, so that the
+    unsigned long long seq;          // host can wait for the result without a D2H copy and a stream synchronisation
     double* S_out;         // device [N] (value-only mode)
     int max_grid;
     int gram_mode;         // 1: nonmonotone gradient slots return h_j = sum_i M_i psi_ij / N (host adds G a)
@@ -92,7 +95,8 @@ cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int
 
 // reduced separable objective: sum log dS, colsum(dPsi/dS) (reference: fun_mon_objective :2978-3018)
 cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* b,
-                              double delta, double* partials, unsigned int* counter, double* out, int max_grid,
+                              double* d_b, double delta, double* partials, unsigned int* counter, double* out,
+                              double* out_host, unsigned long long* flag_host, unsigned long long seq, int max_grid,
                               int sm_count, cudaStream_t st);
 
 struct InvArgs {

@@ -519,6 +519,12 @@ __global__ void __launch_bounds__(T_OBJ) objgrad_kernel(const ObjArgs a) {
             double v = 0.0;
             for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(a.partials + (int64_t)b * (1 + m) + j);
             a.out[j] = v * invN;
+            if (a.out_host) a.out_host[j] = v * invN;
+        }
+        if (a.out_host) {                       // result visible in host memory before the sequence number is
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.flag_host) = a.seq;
         }
         if (tid == 0) *a.counter = 0u;
     }

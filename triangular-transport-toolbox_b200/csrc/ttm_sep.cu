@@ -70,17 +70,24 @@ __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const
 // K-sepobj: out[0] = sum_i log dS_i, out[1+j] = sum_i dpsi_ij / dS_i,
 //           dS_i = sum_j (b_j + delta) dpsi_ij      (transport_map.py:2990-3006)
 // -------------------------------------------------------------------------------------------------
+// b may live in mapped pinned host memory (read once per block); the last block mirrors the result to host memory
+// and publishes the launch's sequence number after a system fence (no D2H copy, no stream synchronisation)
 __global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
-                                                       int64_t N, const double* __restrict__ b, double delta,
-                                                       double* __restrict__ partials, unsigned int* counter,
-                                                       double* __restrict__ out) {
+                                                       int64_t N, const double* __restrict__ b, double* __restrict__ d_b,
+                                                       double delta, double* __restrict__ partials, unsigned int* counter,
+                                                       double* __restrict__ out, double* out_host,
+                                                       unsigned long long* flag_host, unsigned long long seq) {
     extern __shared__ double sm[];
     const int mm = P.m_dmon;
     double* s_b = sm;                 // [mm]
     double* s_acc = sm + mm;          // [mm][T_SEP]
     double* s_red = s_acc + mm * T_SEP;  // [T_SEP/32][1+mm]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int j = tid; j < mm; j += T_SEP) s_b[j] = b[j] + delta;
+    for (int j = tid; j < mm; j += T_SEP) {
+        const double bj = b[j];
+        s_b[j] = bj + delta;
+        if (blockIdx.x == 0 && d_b) d_b[j] = bj;       // device copy of the coefficients (map / inverse use it)
+    }
     for (int j = 0; j < mm; ++j) s_acc[j * T_SEP + tid] = 0.0;
     __syncthreads();
     double lacc = 0.0;
@@ -116,6 +123,12 @@ __global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const d
             double v = 0.0;
             for (unsigned int bk = 0; bk < gridDim.x; ++bk) v += __ldcg(partials + (int64_t)bk * (1 + mm) + j);
             out[j] = v;
+            if (out_host) out_host[j] = v;
+        }
+        if (out_host) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(flag_host) = seq;
         }
         if (tid == 0) *counter = 0u;
     }
@@ -167,7 +180,8 @@ cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld,
 }
 
 cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* b,
-                              double delta, double* partials, unsigned int* counter, double* out, int max_grid,
+                              double* d_b, double delta, double* partials, unsigned int* counter, double* out,
+                              double* out_host, unsigned long long* flag_host, unsigned long long seq, int max_grid,
                               int sm_count, cudaStream_t st) {
     const int mm = P.m_dmon;
     int64_t grid = (N + T_SEP - 1) / T_SEP;
@@ -180,7 +194,8 @@ cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, i
         cudaError_t e = cudaFuncSetAttribute(sepobj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    sepobj_kernel<<<(unsigned)grid, T_SEP, smem, st>>>(P, Xt, ld, N, b, delta, partials, counter, out);
+    sepobj_kernel<<<(unsigned)grid, T_SEP, smem, st>>>(P, Xt, ld, N, b, d_b, delta, partials, counter, out, out_host,
+                                                       flag_host, seq);
     return cudaGetLastError();
 }
 

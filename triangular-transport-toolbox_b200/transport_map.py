@@ -527,6 +527,8 @@ class transport_map():
         self._reset_lazy()
 
     def _reset_lazy(self):
+        self._ensemble_version = getattr(self, '_ensemble_version', 0) + 1   # invalidates cached inverse operands
+        self._inv_fused_cache = None
         self.Psi_nonmon = _LazyList(self.D, lambda k: self._basis(k, 0, self._Xt, self._N))
         self.Psi_mon = _LazyList(self.D, lambda k: self._basis(k, 1, self._Xt, self._N))
         if self.monotonicity.lower() == 'separable monotonicity':
@@ -534,6 +536,7 @@ class transport_map():
         self._fg_cache = {}
         self._gram_nn = {}
         self._gram_donor_G = {}
+        self._sep_donor = {}
 
     def reset(self, X):
         """tm.py:710-748."""
@@ -755,7 +758,9 @@ class transport_map():
                              'success': bool(opt.success)}
         return (opt.x[:div].copy(), opt.x[div:].copy())
 
-    def _gram(self, k):
+    def _gram(self, k, first_col=0):
+        """[Psi_non | Psi_mon]^T [Psi_non | Psi_mon] of component k (K-gram), (M, M).  first_col > 0: only the columns
+        from first_col on are computed (ttm_gram_tail) and returned, (M, M - first_col)."""
         p = self._host_plans[k]
         M = p.m_non + p.m_mon
         G = self._empty(M, M)
@@ -763,39 +768,70 @@ class transport_map():
         need = 64 * Mp * Mp + min(self._N, 1 << 18) * Mp      # split partials + one materialised Psi chunk
         if self._scratch.numel() < need:
             self._scratch = self._empty(need)
-        B.check(self._lib.ttm_gram(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1], self._N,
-                                   B.c_void_p(G.data_ptr()), B.c_void_p(self._scratch.data_ptr()),
-                                   self._scratch.numel(), self._stream()))
+        B.check(self._lib.ttm_gram_tail(self._plans[k], B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1], self._N,
+                                        int(first_col), B.c_void_p(G.data_ptr()), B.c_void_p(self._scratch.data_ptr()),
+                                        self._scratch.numel(), self._stream()))
+        if first_col > 0:
+            G = G[:, first_col:].contiguous()                  # only the computed columns travel to the host
         G = G.cpu().numpy()
         if self._sharded:
             from .parallel import allreduce_sum
             G = allreduce_sum(G.ravel(), self._device).reshape(G.shape)
         return G
 
+    def _separable_donor(self, k):
+        """Shared pieces of the separable setup for every component whose nonmonotone list is a prefix of the donor's
+        (one full K-gram and ONE factorisation per donor instead of one per component): the nonmonotone Gram block
+        and the Cholesky factors of the (Jacobi-scaled) block, of Gnn + lam I and of Gnn + 2 lam I.  The Cholesky
+        factor of a leading principal block is the leading block of the factor."""
+        d = self._gram_donor(k)
+        with self._gram_lock:
+            if d not in self._sep_donor:
+                from scipy.linalg import cholesky
+                md = self._host_plans[d].m_non
+                G = self._gram(d)
+                Gnn = np.ascontiguousarray(G[:md, :md])
+                ent = {'Gnn': Gnn, 'G_full': G}
+                if self.regularization is None:
+                    dv = 1.0 / np.sqrt(np.maximum(np.diag(Gnn), np.finfo(float).tiny))
+                    ent['d'] = dv
+                    ent['L'] = cholesky(Gnn * dv[:, None] * dv[None, :], lower=True, check_finite=False)
+                elif type(self.regularization) == str and self.regularization.lower() == 'l2':
+                    lam = self.regularization_lambda
+                    ent['L1'] = cholesky(Gnn + lam * np.identity(md), lower=True, check_finite=False)
+                    ent['L2'] = cholesky(Gnn + 2 * lam * np.identity(md), lower=True, check_finite=False)
+                self._sep_donor[d] = ent
+        return d, self._sep_donor[d]
+
     def _separable_setup(self, k):
         """Reduced m_mon x m_mon problem from the Gram blocks of [Psi_non | Psi_mon] (K-gram, DMMA).
         No regularisation: A = (Gmm - Gmn Gnn^-1 Gnm)/N, which equals A_sqrt^T A_sqrt / N of the reference's QR
         formulation (tm.py:2966-2975).  L2: the ridge normal equations of tm.py:3031-3050 (no 1/N there)."""
+        from scipy.linalg import solve_triangular
         p = self._host_plans[k]
-        G = self._gram(k)
         mn = p.m_non
-        Gnn, Gnm, Gmm = G[:mn, :mn], G[:mn, mn:], G[mn:, mn:]
+        d, ent = self._separable_donor(k)
+        if d == k:
+            Gt = ent['G_full'][:, mn:]
+        else:
+            Gt = self._gram(k, first_col=mn)                   # Psi^T Psi_mon only: the leading block is the donor's
+        Gnn, Gnm, Gmm = ent['Gnn'][:mn, :mn], Gt[:mn], Gt[mn:]
         N = self._N_global
+        tri = lambda L, rhs, trans=0: solve_triangular(L, rhs, lower=True, trans=trans, check_finite=False)
         if self.regularization is None:
             # scaled Cholesky solve (Jacobi preconditioning tames the squared condition number)
-            from scipy.linalg import cholesky, solve_triangular
-            d = 1.0 / np.sqrt(np.maximum(np.diag(Gnn), np.finfo(float).tiny))
-            L = cholesky(Gnn * d[:, None] * d[None, :], lower=True, overwrite_a=True, check_finite=False)
-            Y = solve_triangular(L, Gnm * d[:, None], lower=True, check_finite=False)
+            dv, L = ent['d'][:mn], ent['L'][:mn, :mn]
+            Y = tri(L, Gnm * dv[:, None])
             A = (Gmm - Y.T @ Y) / N
-            back = lambda b: -(d * solve_triangular(L, Y @ b, lower=True, trans='T', check_finite=False))
+            back = lambda b: -(dv * tri(L, Y @ b, 'T'))
         elif self.regularization.lower() == 'l2':
             lam = self.regularization_lambda
-            Bm = np.linalg.solve(Gnn + lam * np.identity(mn), Gnm)
+            L1, L2 = ent['L1'][:mn, :mn], ent['L2'][:mn, :mn]
+            Bm = tri(L1, tri(L1, Gnm), 'T')                    # (Gnn + lam I)^-1 Gnm
             # (Psi_m - Psi_n B)^T (Psi_m - Psi_n B) expanded in Gram blocks
             R = Gmm - Gnm.T @ Bm - Bm.T @ Gnm + Bm.T @ Gnn @ Bm
             A = R / 2 + lam * (Bm.T @ Bm + np.identity(Bm.shape[-1]))
-            back = lambda b: -np.linalg.solve(Gnn + 2 * lam * np.identity(mn), Gnm @ b)
+            back = lambda b: -tri(L2, tri(L2, Gnm @ b), 'T')
         else:
             raise ValueError("separable monotonicity supports regularization None or 'l2'")
         return 0.5 * (A + A.T), back
@@ -974,6 +1010,17 @@ class transport_map():
             return None
         from .plan import FAM_HERMITE_E
         ks = [k for _, k in comps]
+        # operands depend on the coefficients and the special-term placement only: repeated calls (sampling in batches,
+        # the chunks of one call) reuse them
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        for k in ks:
+            h.update(np.ascontiguousarray(self.coeffs_nonmon[k], dtype=np.float64).tobytes())
+            h.update(np.ascontiguousarray(self.coeffs_mon[k], dtype=np.float64).tobytes())
+        key = (tuple(ks), resolution, self._ensemble_version, h.digest())
+        hit = getattr(self, '_inv_fused_cache', None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         plans = [self._host_plans[k] for k in ks]
         c0 = plans[0].c
         if self._family != FAM_HERMITE_E or any(p.c != c0 + j for j, p in enumerate(plans)):
@@ -1016,8 +1063,10 @@ class transport_map():
                 return None
             dst, src, sc = cache[key]
             A[dst] = cn[src] * sc
-        return {'ncomp': ncomp, 'c0': c0, 'ns': ns, 'A': self._upload(A), 'a0': self._upload(a0),
-                'tabs': self._monotone_tables(comps, resolution=resolution), 'ntab': resolution}
+        fused = {'ncomp': ncomp, 'c0': c0, 'ns': ns, 'A': self._upload(A), 'a0': self._upload(a0),
+                 'tabs': self._monotone_tables(comps, resolution=resolution), 'ntab': resolution}
+        self._inv_fused_cache = (key, fused)
+        return fused
 
     def _inverse_fused_launch(self, f, Xw, ld, n, Zt, ldz, stream=None):
         B.check(self._lib.ttm_inverse_fused(self._ctx, B.c_void_p(Xw.data_ptr()), ld, n, B.c_void_p(Zt.data_ptr()), ldz,
