@@ -43,6 +43,9 @@ typedef struct ttm_plan ttm_plan; /* one compiled map component (term tables + w
 const char* ttm_last_error(void);
 int ttm_version(void);
 
+/* 1 if host_ptr lies in page-locked (pinned / registered) host memory: such inputs are copied to the device directly,
+ * pageable ones through the library's pinned staging buffers */
+int ttm_host_is_pinned(const void* host_ptr, int* host_out);
 /* device query used by the host to size grids and scratch buffers */
 int ttm_device_sm_count(int device, int* host_sm_count);
 

@@ -193,3 +193,58 @@ def test_pipelined_inverse_is_bit_identical_to_one_shot(conditioning, monkeypatc
     piped = tm.inverse_map(Z, X_star=Xs)
     assert piped.shape == one_shot.shape
     assert np.array_equal(piped, one_shot)
+
+
+@pytest.mark.parametrize('D,E,n', [(20, 3, 301), (17, 0, 64), (33, 16, 1000)])
+def test_fused_inverse_block_edges_match_the_oracle(D, E, n):
+    """K-inv-fused walks the components in blocks of 16 and the samples in tiles of 256: component counts of 17
+    (one full block + one component), 16 + 1 with an empty conditioning block, ragged sample counts."""
+    from cases import c5_terms, headline_sep_coeffs
+    mon, non = c5_terms(D)
+    X = synthetic_samples(400, D, seed=21)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+    tm = make_cuda(X.copy(), **kw)
+    om = make_oracle(X.copy(), **kw)
+    cm, cn = headline_sep_coeffs(mon, non)
+    for k in range(D):
+        tm.coeffs_mon[k], tm.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
+        om.coeffs_mon[k], om.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
+    rng = np.random.default_rng(5)
+    Z = rng.standard_normal((n, D - E))
+    Xs = synthetic_samples(n, D, seed=22)[:, :E].copy() if E else None
+    assert tm._inverse_fused_setup([(i, k) for i, k in enumerate(range(E, D))]) is not None
+    assert rel_err(tm.inverse_map(Z.copy(), None if Xs is None else Xs.copy()),
+                   om.inverse_map(Z.copy(), None if Xs is None else Xs.copy())) <= 1e-10
+
+
+@pytest.mark.parametrize('name', ['sep_ex05', 'sep_ex06_cycle', 'sep_c5_d6'])
+def test_per_component_paths_match_the_fused_ones(name, monkeypatch):
+    """map / inverse_map / densities through the per-component kernels (TTM_MAP_FUSED=0, TTM_INV_FUSED=0: the paths
+    large or out-of-class maps take) against the reference fixtures, like the fused default."""
+    import os
+    from cases import cases
+    from harness import run_case
+    monkeypatch.setenv('TTM_MAP_FUSED', '0')
+    monkeypatch.setenv('TTM_INV_FUSED', '0')
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name + '.npz'))
+    res = run_case(lambda X, **kw: make_cuda(X, **{k: v for k, v in kw.items() if k != 'verbose'}), cases()[name], fitted=gold)
+    for key in ('map_X', 'map_train', 'inverse_table', 'pullback', 'pushforward'):
+        if key in res:
+            assert rel_err(res[key], gold[key]) <= 1e-9, (name, key)
+
+
+def test_x_setter_invalidates_memoised_objective():
+    """assigning tm.X must drop the memoised (J, grad), the Gram matrices and the lazy Psi."""
+    X = synthetic_samples(600, 3, seed=30)
+    mon, non = c4_terms(3)
+    tm = make_cuda(X.copy(), monotone=mon, nonmonotone=non, monotonicity='integrated rectifier',
+                   quadrature_input={'order': 12}, standardize_samples=False)
+    c = np.random.default_rng(1).standard_normal(len(non[2]) + len(mon[2])) * 0.1
+    f0 = tm.objective_function(c, 2, len(non[2]))
+    X2 = synthetic_samples(700, 3, seed=31)
+    tm.X = X2.copy()
+    fresh = make_cuda(X2.copy(), monotone=mon, nonmonotone=non, monotonicity='integrated rectifier',
+                      quadrature_input={'order': 12}, standardize_samples=False)
+    f1 = tm.objective_function(c, 2, len(non[2]))
+    assert f1 != f0 and abs(f1 - fresh.objective_function(c, 2, len(non[2]))) <= 1e-13
+    assert rel_err(tm.objective_function_jacobian(c, 2, len(non[2])), fresh.objective_function_jacobian(c, 2, len(non[2]))) <= 1e-12

@@ -34,6 +34,7 @@ def lib():
         L.ttm_last_error.restype = ctypes.c_char_p
         sig = {
             'ttm_device_sm_count': [c_int, ctypes.POINTER(c_int)],
+            'ttm_host_is_pinned': [c_void_p, ctypes.POINTER(c_int)],
             'ttm_ctx_create': [c_int, ctypes.POINTER(c_void_p)],
             'ttm_ctx_destroy': [c_void_p],
             'ttm_ctx_set_quadrature': [c_void_p, _dp, _dp, c_int],

@@ -35,7 +35,7 @@ constexpr int MAX_GRID = 160 * 8;   // rows of the per-plan partials buffer (>= 
 
 struct ttm_ctx {
     int device = 0;
-    int sm_count = 148;
+    int sm_count = 0;         // cudaDeviceProp::multiProcessorCount of `device` (ttm_ctx_create)
     int Q = 0;
     double wsum = 0.0;
     double* d_xis = nullptr;
@@ -76,6 +76,15 @@ extern "C" {
 
 const char* ttm_last_error(void) { return g_err.c_str(); }
 int ttm_version(void) { return 100; }
+
+int ttm_host_is_pinned(const void* host_ptr, int* host_out) {
+    if (!host_ptr || !host_out) return fail(TTM_ERR_ARG, "ttm_host_is_pinned: null argument");
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, host_ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); *host_out = 0; return TTM_OK; }   // ordinary pageable memory
+    *host_out = (at.type == cudaMemoryTypeHost) ? 1 : 0;
+    return TTM_OK;
+}
 
 int ttm_device_sm_count(int device, int* host_sm_count) {
     cudaDeviceProp p;
@@ -408,7 +417,7 @@ int ttm_sep_eval(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, double* S
     if (!p || N <= 0 || (S_out && (!Xt || ld < N)) || (dS_out && (!Xd || ldd < N)))
         return fail(TTM_ERR_ARG, "ttm_sep_eval: bad arguments");
     CK(cudaSetDevice(p->ctx->device));
-    CK(ttm_launch_sep_eval(p->view, Xt, ld, N, p->d_coeffs, S_out, Xd, ldd, dS_out, (cudaStream_t)stream));
+    CK(ttm_launch_sep_eval(p->view, Xt, ld, N, p->d_coeffs, S_out, Xd, ldd, dS_out, p->ctx->sm_count, (cudaStream_t)stream));
     return TTM_OK;
 }
 
@@ -527,7 +536,7 @@ int ttm_inverse_table(ttm_plan* p, double* Xt, int64_t ld, int64_t N, const doub
     fill_inv(p, Xt, ld, N, z, a);
     a.separable = 1;
     a.table = table; a.ntab = ntab; a.truncate = truncate;
-    CK(ttm_launch_inverse_table(a, (cudaStream_t)stream));
+    CK(ttm_launch_inverse_table(a, p->ctx->sm_count, (cudaStream_t)stream));
     return TTM_OK;
 }
 
@@ -567,11 +576,11 @@ int ttm_inverse_bisect(ttm_plan* p, double* Xt, int64_t ld, int64_t N, const dou
     // samples 1..N-1 first; sample 0 then iterates only as long as any of them did
     // (the reference's loop condition sums the remaining *indices*, tm.py:3952)
     a.first = 1; a.count = N - 1;
-    cudaError_t e = ttm_launch_inverse_bisect(a, st);
+    cudaError_t e = ttm_launch_inverse_bisect(a, c->sm_count, st);
     if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_inverse_bisect: polynomial order > 32 or > 16 special inner terms");
     CK(e);
     a.first = 0; a.count = 1;
-    CK(ttm_launch_inverse_bisect(a, st));
+    CK(ttm_launch_inverse_bisect(a, c->sm_count, st));
     if (host_not_converged) {
         CK(cudaMemcpyAsync(host_not_converged, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

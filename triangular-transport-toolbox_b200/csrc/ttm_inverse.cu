@@ -223,11 +223,11 @@ __global__ void mon_table_kernel(const PlanView P, const double* __restrict__ co
 
 }  // namespace
 
-cudaError_t ttm_launch_inverse_table(const InvArgs& a, cudaStream_t st) {
+cudaError_t ttm_launch_inverse_table(const InvArgs& a, int sm_count, cudaStream_t st) {
     if (a.N == 0) return cudaSuccess;
     const int64_t rows = (a.N + T_INV - 1) / T_INV;
     int64_t grid = (rows + R_OBJ - 1) / R_OBJ;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
     const size_t smem = sizeof(double) * (size_t)(a.P.m_non + a.P.m_mon + 2 * a.ntab + dense_smem_doubles(a.P.ndense, a.P.dense_maxord));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(inverse_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -237,12 +237,12 @@ cudaError_t ttm_launch_inverse_table(const InvArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t ttm_launch_inverse_bisect(const InvArgs& a, cudaStream_t st) {
+cudaError_t ttm_launch_inverse_bisect(const InvArgs& a, int sm_count, cudaStream_t st) {
     if (a.count == 0) return cudaSuccess;
     if (2 * (a.P.maxord + 1) + a.P.nst > MAX_SLOTS) return cudaErrorInvalidValue;
     const int64_t rows = (a.count + T_INV - 1) / T_INV;
     int64_t grid = (rows + R_OBJ - 1) / R_OBJ;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
     const size_t smem = sizeof(double) * (size_t)(a.P.m_non + a.P.m_mon + 2 * a.Q + dense_smem_doubles(a.P.ndense, a.P.dense_maxord));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(inverse_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

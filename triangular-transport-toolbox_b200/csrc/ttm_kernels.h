@@ -63,7 +63,8 @@ cudaError_t ttm_launch_basis_concat(const PlanView& P, const double* Xt, int64_t
 
 // separable-monotonicity evaluation: S_k and d_k S_k per sample (reference: s :2550-2558, densities :2620-2641)
 cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* coeffs,
-                                double* S_out, const double* Xd, int64_t ldd, double* dS_out, cudaStream_t st);
+                                double* S_out, const double* Xd, int64_t ldd, double* dS_out, int sm_count,
+                                cudaStream_t st);
 
 cudaError_t ttm_launch_density_acc(double* acc, const double* S, const double* dS, double sigma, int mode, int64_t N,
                                    cudaStream_t st);
@@ -140,8 +141,8 @@ struct InvFusedArgs {
 cudaError_t ttm_launch_inverse_fused(const InvFusedArgs& a, int sm_count, cudaStream_t st);
 size_t ttm_inverse_fused_apack_doubles(int ncomp, int c0, int ns);
 
-cudaError_t ttm_launch_inverse_table(const InvArgs& a, cudaStream_t st);
-cudaError_t ttm_launch_inverse_bisect(const InvArgs& a, cudaStream_t st);
+cudaError_t ttm_launch_inverse_table(const InvArgs& a, int sm_count, cudaStream_t st);
+cudaError_t ttm_launch_inverse_bisect(const InvArgs& a, int sm_count, cudaStream_t st);
 cudaError_t ttm_launch_mon_table(const PlanView& P, const double* coeffs, int ntab, double lo, double hi,
                                  double* table, cudaStream_t st);
 

@@ -133,32 +133,38 @@ constexpr int BD_MAXORD = 1 << 20;   // no limit: the ladder is a two-term state
 __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
                                                             int64_t N, double* __restrict__ Psi, int64_t ldp, int coff) {
     __shared__ double tile[TJ_BAS][T_BAS + 1];
-    extern __shared__ int s_t2e[];               // term -> dense entry (group * stride + slot), -1: constant
+    extern __shared__ double s_dyn[];            // per term: scale [m] | packed {column : 20, order : 10, hf : 1, valid : 1} [m]
     const int m = P.m_non;
+    double* s_scale = s_dyn;
+    int* s_meta = reinterpret_cast<int*>(s_dyn + m);
     const int stride = 2 * (P.dense_maxord + 1);
-    for (int j = threadIdx.x; j < m; j += T_BAS) s_t2e[j] = -1;
+    for (int j = threadIdx.x; j < m; j += T_BAS) { s_meta[j] = 0; s_scale[j] = 1.0; }   // default: constant term
     __syncthreads();
     for (int e = threadIdx.x; e < P.ndense * stride; e += T_BAS) {
         const int j = P.ib[P.o_dense_idx + e];
-        if (j >= 0) s_t2e[j] = e;
+        if (j >= 0) {
+            const int g = e / stride, slot = e - g * stride;
+            s_meta[j] = (1 << 31) | ((slot & 1) << 30) | ((slot >> 1) << 20) | P.ib[P.o_dense_var + 4 * g];
+            s_scale[j] = P.db[P.o_d_dense_scale + e];
+        }
     }
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * T_BAS;
     const int64_t i = base + threadIdx.x;
     const int64_t ic = i < N ? i : N - 1;
-    int last_g = -1, cur = 0;                    // cached group; ladder state: pc = P_cur(x), pm = P_{cur-1}(x)
+    int last_col = -1, cur = 0;                  // cached column; ladder state: pc = P_cur(x), pm = P_{cur-1}(x)
     double x = 0.0, ga = 0.0, pc = 1.0, pm = 0.0;
     bool have_ga = false;
     for (int j0 = 0; j0 < m; j0 += TJ_BAS) {
         const int w = min(TJ_BAS, m - j0);
         for (int t = 0; t < w; ++t) {
-            const int e = s_t2e[j0 + t];
+            const int meta = s_meta[j0 + t];
             double v = 1.0;                      // constant term (np.ones, tm.py:890)
-            if (e >= 0) {
-                const int g = e / stride, slot = e - g * stride, o = slot >> 1;
-                if (g != last_g) {
-                    x = Xt[(int64_t)P.ib[P.o_dense_var + 4 * g] * ld + ic];
-                    last_g = g; cur = 0; pc = 1.0; pm = 0.0; have_ga = false;
+            if (meta < 0) {
+                const int col = meta & 0xfffff, o = (meta >> 20) & 0x3ff;
+                if (col != last_col) {
+                    x = Xt[(int64_t)col * ld + ic];
+                    last_col = col; cur = 0; pc = 1.0; pm = 0.0; have_ga = false;
                 }
                 if (o < cur) { cur = 0; pc = 1.0; pm = 0.0; }   // orders usually ascend within a variable
                 for (; cur < o; ++cur) {         // three-term recurrence of the family up to order o
@@ -167,8 +173,8 @@ __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, co
                     const double pn = fma(fma(A, x, B), pc, -C * pm);
                     pm = pc; pc = pn;
                 }
-                v = P.db[P.o_d_dense_scale + e] * pc;
-                if (slot & 1) {
+                v = s_scale[j0 + t] * pc;
+                if (meta & (1 << 30)) {
                     if (!have_ga) { ga = exp(-0.25 * x * x); have_ga = true; }
                     v *= ga;
                 }
@@ -176,9 +182,16 @@ __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, co
             tile[t][threadIdx.x] = v;
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < w * T_BAS; e += T_BAS) {
-            const int s = e / w, t = e - s * w;
-            if (base + s < N) Psi[(base + s) * ldp + coff + j0 + t] = tile[t][s];
+        if (w == TJ_BAS) {                       // full window: 16 consecutive terms of one sample = 128 contiguous bytes
+            for (int e = threadIdx.x; e < TJ_BAS * T_BAS; e += T_BAS) {
+                const int s = e >> 4, t = e & 15;
+                if (base + s < N) Psi[(base + s) * ldp + coff + j0 + t] = tile[t][s];
+            }
+        } else {
+            for (int e = threadIdx.x; e < w * T_BAS; e += T_BAS) {
+                const int s = e / w, t = e - s * w;
+                if (base + s < N) Psi[(base + s) * ldp + coff + j0 + t] = tile[t][s];
+            }
         }
         __syncthreads();
     }
@@ -237,8 +250,8 @@ cudaError_t ttm_launch_basis(const PlanView& P, int which, const double* Xt, int
     else if (which == 1) { o_ptr = P.o_mon_ptr; o_fac = P.o_mon_fac; m = P.m_mon; }
     else { o_ptr = P.o_dmon_ptr; o_fac = P.o_dmon_fac; m = P.m_dmon; }
     if (m == 0 || N == 0) return cudaSuccess;
-    if (which == 0 && P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && m * sizeof(int) <= 40 * 1024)
-        basis_dense_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, m * sizeof(int), st>>>(P, Xt, ld, N, Psi, m, 0);
+    if (which == 0 && P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && m * 12 <= 30 * 1024)
+        basis_dense_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, m * 12, st>>>(P, Xt, ld, N, Psi, m, 0);
     else
         basis_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, 0, st>>>(P, o_ptr, o_fac, m, Xt, ld, N, Psi, m, 0);
     return cudaGetLastError();
@@ -250,8 +263,8 @@ cudaError_t ttm_launch_basis_concat(const PlanView& P, const double* Xt, int64_t
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + T_BAS - 1) / T_BAS);
     if (P.m_non > 0) {
-        if (P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && P.m_non * sizeof(int) <= 40 * 1024)
-            basis_dense_kernel<<<grid, T_BAS, P.m_non * sizeof(int), st>>>(P, Xt, ld, n, Psi, ldp, 0);
+        if (P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && P.m_non * 12 <= 30 * 1024)
+            basis_dense_kernel<<<grid, T_BAS, P.m_non * 12, st>>>(P, Xt, ld, n, Psi, ldp, 0);
         else
             basis_kernel<<<grid, T_BAS, 0, st>>>(P, P.o_non_ptr, P.o_non_fac, P.m_non, Xt, ld, n, Psi, ldp, 0);
     }

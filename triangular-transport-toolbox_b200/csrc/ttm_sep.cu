@@ -165,11 +165,12 @@ cudaError_t ttm_launch_density_finish(const double* acc, const double* logt, dou
 }
 
 cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* coeffs,
-                                double* S_out, const double* Xd, int64_t ldd, double* dS_out, cudaStream_t st) {
+                                double* S_out, const double* Xd, int64_t ldd, double* dS_out, int sm_count,
+                                cudaStream_t st) {
     if (N == 0) return cudaSuccess;
     const int64_t rows = (N + T_SEP - 1) / T_SEP;
     int64_t grid = (rows + R_OBJ - 1) / R_OBJ;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
     const size_t smem = sizeof(double) * (size_t)(P.m_non + P.m_mon + dense_smem_doubles(P.ndense, P.dense_maxord));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(sep_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

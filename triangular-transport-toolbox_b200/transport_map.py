@@ -749,13 +749,22 @@ class transport_map():
     def worker_task(self, k, task_supervisor=None):
         """BFGS on the fused objective/gradient (tm.py:3174-3298)."""
         from scipy.optimize import minimize
+        import time as _time
         div = len(self.coeffs_nonmon[k])
         x0 = np.concatenate((self.coeffs_nonmon[k], self.coeffs_mon[k]))
-        opt = minimize(method='BFGS', fun=self.objective_function, jac=self.objective_function_jacobian,
-                       x0=x0, args=(k, div))
+        _t0 = _time.perf_counter()
+        from . import hostopt
+        if os.environ.get('TTM_HOST_OPT', 'native') != 'scipy' and hostopt.available():
+            # the same BFGS iteration with scipy's own line search and an O(n^2) update (hostopt.py): scipy's O(n^3)
+            # update costs more than the CUDA evaluation once a component has a few hundred coefficients
+            opt = hostopt.quasi_newton(lambda c: (self.objective_function(c, k, div),
+                                                  self.objective_function_jacobian(c, k, div)), x0)
+        else:
+            opt = minimize(method='BFGS', fun=self.objective_function, jac=self.objective_function_jacobian,
+                           x0=x0, args=(k, div))
         self._last_opt = opt
         self._fit_info[k] = {'nit': int(opt.nit), 'nfev': int(opt.nfev), 'fun': float(opt.fun),
-                             'success': bool(opt.success)}
+                             'success': bool(opt.success), 'seconds': _time.perf_counter() - _t0}
         return (opt.x[:div].copy(), opt.x[div:].copy())
 
     def _gram(self, k, first_col=0):
@@ -1141,6 +1150,14 @@ class transport_map():
             return [pool.submit(np.copyto, dst[edges[t]:edges[t + 1]], src[edges[t]:edges[t + 1]])
                     for t in range(nthr) if edges[t + 1] > edges[t]]
 
+        def pinned(a):                                       # caller's array already page-locked: DMA straight from it
+            if a is None or not a.flags['C_CONTIGUOUS'] or a.dtype != np.float64:
+                return False
+            flag = B.c_int(0)
+            B.check(lib.ttm_host_is_pinned(B.c_void_p(a.ctypes.data), B.ctypes.byref(flag)))
+            return bool(flag.value)
+        z_pinned, x_pinned = pinned(Z), pinned(X_star)
+
         with ThreadPoolExecutor(nthr) as pool:
             for c in range(nchunk):
                 c0, c1 = c * cap, min(N, (c + 1) * cap)
@@ -1150,20 +1167,22 @@ class transport_map():
                 sl = slots[c % nslot]
                 if sl['event'] is not None:
                     sl['event'].synchronize()                # the slot's previous chunk is back on the host
-                futs = stage(sl['hz'].numpy(), Z[c0:c1], n)
-                if E > 0:
+                futs = [] if z_pinned else stage(sl['hz'].numpy(), Z[c0:c1], n)
+                if E > 0 and not x_pinned:
                     futs += stage(sl['hx'].numpy(), X_star[c0:c1], n)
                 for f in futs:
                     f.result()
+                src_z = torch.from_numpy(Z[c0:c1]) if z_pinned else sl['hz'][:n]
+                src_x = (torch.from_numpy(X_star[c0:c1]) if x_pinned else sl['hx'][:n]) if E > 0 else None
                 with torch.cuda.stream(sl['stream']):
                     st = self._stream()
-                    sl['dz'][:n].copy_(sl['hz'][:n], non_blocking=True)
+                    sl['dz'][:n].copy_(src_z, non_blocking=True)
                     B.check(lib.ttm_standardize_transpose(self._ctx, ptr(sl['dz']), n, nz, None, None,
                                                           ptr(sl['Zt']), cap, st))
                     if E < skip:                             # unconditioned leading columns read as zero
                         sl['Xw'][E:skip].zero_()
                     if E > 0:
-                        sl['dx'][:n].copy_(sl['hx'][:n], non_blocking=True)
+                        sl['dx'][:n].copy_(src_x, non_blocking=True)
                         B.check(lib.ttm_standardize_transpose(self._ctx, ptr(sl['dx']), n, E, ptr(mean_in), ptr(std_in),
                                                               ptr(sl['Xw']), cap, st))
                     if fused is not None:
