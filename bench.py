@@ -612,16 +612,16 @@ def run_gpu(args):
             g = tm.objective_function_jacobian(c, k, div)
         return f + g[0]
 
-    def step_e2e(s):
-        """Public class API from two host threads (what optimize() does): host coefficients in, host (J, grad) out."""
-        return sum(pool.map(eval_one, [(k, s) for k in mine]))
+    def run_e2e(steps):
+        """Public class API from two host threads (what optimize() does): host coefficients in, host (J, grad) out.
+        The evaluations of all steps form one queue (no barrier between steps: the 64 evaluations are independent and
+        so are the steps); every evaluation is a complete host -> device -> host round trip."""
+        return sum(pool.map(eval_one, [(k, s) for s in steps for k in mine]))
 
-    for s in range(args.warmup):
-        step_e2e(-s - 1)
+    run_e2e([-s - 1 for s in range(args.warmup)])
     barrier()
     w0 = time.perf_counter()
-    for s in range(args.steps):
-        step_e2e(s)
+    run_e2e(list(range(args.steps)))
     torch.cuda.synchronize()
     t_e2e_local = time.perf_counter() - w0
     pool.shutdown()

@@ -193,6 +193,21 @@ def test_pipelined_inverse_is_bit_identical_to_one_shot(conditioning, monkeypatc
     piped = tm.inverse_map(Z, X_star=Xs)
     assert piped.shape == one_shot.shape
     assert np.array_equal(piped, one_shot)
+    # the same call with the inputs in page-locked host memory: copied to the device directly, no staging
+    import torch
+    from ttt_b200 import binding as B
+    Zp = torch.empty(Z.shape, dtype=torch.float64, pin_memory=True).numpy()
+    Zp[:] = Z
+    flag = B.c_int(0)
+    B.check(tm._lib.ttm_host_is_pinned(B.c_void_p(Zp.ctypes.data), B.ctypes.byref(flag)))
+    assert flag.value == 1
+    B.check(tm._lib.ttm_host_is_pinned(B.c_void_p(Z.ctypes.data), B.ctypes.byref(flag)))
+    assert flag.value == 0
+    Xp = None
+    if Xs is not None:
+        Xp = torch.empty(Xs.shape, dtype=torch.float64, pin_memory=True).numpy()
+        Xp[:] = Xs
+    assert np.array_equal(tm.inverse_map(Zp, X_star=Xp), one_shot)
 
 
 @pytest.mark.parametrize('D,E,n', [(20, 3, 301), (17, 0, 64), (33, 16, 1000)])
@@ -248,3 +263,16 @@ def test_x_setter_invalidates_memoised_objective():
     f1 = tm.objective_function(c, 2, len(non[2]))
     assert f1 != f0 and abs(f1 - fresh.objective_function(c, 2, len(non[2]))) <= 1e-13
     assert rel_err(tm.objective_function_jacobian(c, 2, len(non[2])), fresh.objective_function_jacobian(c, 2, len(non[2]))) <= 1e-12
+
+
+def test_standardize_method_matches_the_oracle():
+    """tm.standardize() (tm.py:750-787) on a map built with standardize_samples=False."""
+    X = synthetic_samples(500, 3, seed=40) * np.array([2.0, 0.3, 5.0]) + np.array([1.0, -2.0, 0.5])
+    mon, non = c4_terms(3)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='integrated rectifier', standardize_samples=False)
+    tm = make_cuda(X.copy(), quadrature_input={'order': 10}, **kw)
+    om = make_oracle(X.copy(), quadrature_input={'order': 10}, **kw)
+    tm.standardize()
+    om.standardize()
+    assert rel_err(tm.X_mean, om.X_mean) <= 1e-12 and rel_err(tm.X_std, om.X_std) <= 1e-12
+    assert rel_err(tm.X, om.X) <= 1e-12

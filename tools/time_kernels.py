@@ -85,6 +85,15 @@ if tm._scratch.numel() < need:
 t = timeit(lambda: B.check(lib.ttm_gram(tm._plans[k], Xp, ld, ng, B.c_void_p(G.data_ptr()),
                                         B.c_void_p(tm._scratch.data_ptr()), tm._scratch.numel(), st)), reps=3)
 out['gram'] = {'ms': t * 1e3, 'TFLOPs': 2.0 * ng * M * M / t / 1e12, 'n': ng, 'M': M}
+out['gram_sizes'] = []
+for ng2 in (10_000, 200_000):
+    if ng2 <= N:
+        t2 = timeit(lambda: B.check(lib.ttm_gram(tm._plans[k], Xp, ld, ng2, B.c_void_p(G.data_ptr()),
+                                                 B.c_void_p(tm._scratch.data_ptr()), tm._scratch.numel(), st)), reps=3)
+        out['gram_sizes'].append({'n': ng2, 'M': M, 'ms': t2 * 1e3, 'TFLOPs': 2.0 * ng2 * M * M / t2 / 1e12})
+tt = timeit(lambda: B.check(lib.ttm_gram_tail(tm._plans[k], Xp, ld, ng, p.m_non, B.c_void_p(G.data_ptr()),
+                                              B.c_void_p(tm._scratch.data_ptr()), tm._scratch.numel(), st)), reps=3)
+out['gram_tail'] = {'ms': tt * 1e3, 'n': ng, 'M': M, 'first_col': p.m_non}
 
 # K-inv-table / K-inv-bisect for the last component (columns < k solved = the training columns)
 z = tm._upload(rng.standard_normal(N))

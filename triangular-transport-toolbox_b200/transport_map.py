@@ -550,7 +550,17 @@ class transport_map():
         self.precalculate()
 
     def standardize(self):
-        raise NotImplementedError("standardisation happens on the device inside reset()/__init__ (K-std)")
+        """tm.py:750-787: standardise the stored samples in place (mean/std or median/quantile spread) and record
+        X_mean / X_std.  The constructor and reset() do this on the way in (K-std); calling it again treats the
+        currently stored samples as raw, exactly like the reference."""
+        raw = np.array(self.X)
+        keep = self.standardize_samples
+        self.standardize_samples = True
+        try:
+            self._load_samples(raw)
+        finally:
+            self.standardize_samples = keep
+        self._reset_lazy()
 
     # ================================================================== forward map
     def _set_coeffs(self, k, coeffs_nonmon, coeffs_mon):
