@@ -232,10 +232,12 @@ def inverse_metric(rank, world, dist, torch, with_cpu=False):
         Xw[:E] = torch.randn(E, ns, dtype=torch.float64, device='cuda', generator=g)
         Zt = torch.randn(Dm - E, ns, dtype=torch.float64, device='cuda', generator=g)
         ts = []
+        base = (torch.empty(Dm - E, (ns + 1) // 2 * 2, dtype=torch.float64, device='cuda')
+                if fused.get('R') is not None else None)           # scratch of K-inv-rect
         for rep in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            tm._inverse_fused_launch(fused, Xw, ns, ns, Zt, ns)
+            tm._inverse_fused_launch(fused, Xw, ns, ns, Zt, ns, base=base)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)

@@ -166,6 +166,11 @@ int ttm_gram_tail(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, int f
  * dS_i = sum_j (b_j + delta) dPsi_ij.  The m_mon x m_mon algebra with A stays on the host.       */
 int ttm_sep_objgrad(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, const double* host_b,
                     double* host_out, void* stream);
+/* the same in two halves, so that the independent components' L-BFGS-B iterations (Pool.map over worker_task_monotone,
+ * tm.py:2837-2845) advance in lockstep: launch every component that wants (f, g), then collect them all.  One launch
+ * per plan may be outstanding. */
+int ttm_sep_objgrad_launch(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, const double* host_b, void* stream);
+int ttm_sep_objgrad_wait(ttm_plan* plan, double* host_out, void* stream);
 
 /* ---- K-inv -----------------------------------------------------------------------------------
  * replaces: vectorized_root_search_alternate tm.py:3987-4084 (table) and
@@ -188,6 +193,16 @@ int ttm_inverse_fused_apack_size(int ncomp, int c0, int ns, int64_t* host_double
 int ttm_inverse_fused(ttm_ctx* ctx, double* Xw, int64_t ld, int64_t N, const double* Zt, int64_t ldz, int ncomp, int c0,
                       int ns, const double* Apack, const double* a0, const double* tables, int ntab, int truncate,
                       void* stream);
+/* The same result in two launches for a conditional inverse with a wide conditioning block (X_star given, c0 > 0):
+ * K-inv-rect first contracts the c0 known columns with every component's coefficients as one tall-skinny FP64 GEMM,
+ * base[j][i] = sum_{v<c0} sum_q f_q(x_iv) Rpack[j/128][v][q][j%128] (features formed once per sample and variable
+ * instead of once per block of 16 components), then K-inv-fused starts from `base` and walks only the columns it
+ * solves.  Rpack (ttm_inverse_rect_rpack_size doubles) = [ceil(ncomp/128)][c0 rounded up to 8][ns][128], zero padded;
+ * base = device scratch [ncomp][ldb], 16-byte aligned, ldb even and >= N. */
+int ttm_inverse_rect_rpack_size(int ncomp, int c0, int ns, int64_t* host_doubles);
+int ttm_inverse_fused_split(ttm_ctx* ctx, double* Xw, int64_t ld, int64_t N, const double* Zt, int64_t ldz, int ncomp,
+                            int c0, int ns, const double* Apack, const double* Rpack, const double* a0,
+                            const double* tables, int ntab, int truncate, double* base, int64_t ldb, void* stream);
 /* separable != 0: monotone part is linear in the coefficients; else Gauss-Legendre of the rectifier.
  * host_not_converged receives the number of samples stopped at max_iter (the reference warns).   */
 int ttm_inverse_bisect(ttm_plan* plan, double* Xt, int64_t ld, int64_t N, const double* z, int separable,

@@ -232,6 +232,38 @@ def test_fused_inverse_block_edges_match_the_oracle(D, E, n):
                    om.inverse_map(Z.copy(), None if Xs is None else Xs.copy())) <= 1e-10
 
 
+@pytest.mark.parametrize('D,E,n,mixed', [(21, 9, 333, False), (40, 7, 64, False), (150, 5, 130, False),
+                                         (48, 33, 1, False), (20, 6, 300, True), (14, 0, 77, True)])
+def test_split_inverse_matches_the_oracle(D, E, n, mixed, monkeypatch):
+    """K-inv-rect + K-inv-fused (TTM_INV_SPLIT=1: conditioning block contracted as a GEMM first): conditioning widths
+    that are not multiples of the 8-variable chunk, sample counts that are not multiples of the 64-sample tile (odd,
+    below one tile, a single sample), more than 128 solved components (two component tiles)."""
+    from cases import c5_terms, headline_sep_coeffs
+    monkeypatch.setenv('TTM_INV_SPLIT', '1')
+    mon, non = c5_terms(D)
+    if mixed:                                   # plain and Hermite-function terms of every order: the 6-slot operands
+        non = [[[]] + [t for j in range(k) for t in ([j], [j, 'HF'], [j, j], [j, j, 'HF'], [j, j, j], [j, j, j, 'HF'])]
+               for k in range(D)]
+    X = synthetic_samples(400, D, seed=23)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+    tm = make_cuda(X.copy(), **kw)
+    om = make_oracle(X.copy(), **kw)
+    cm, cn = headline_sep_coeffs(mon, non)
+    for k in range(D):
+        tm.coeffs_mon[k], tm.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
+        om.coeffs_mon[k], om.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
+    Z = np.random.default_rng(6).standard_normal((n, D - E))
+    Xs = synthetic_samples(n, D, seed=24)[:, :E].copy() if E else None
+    xs = lambda: None if Xs is None else Xs.copy()
+    fz = tm._inverse_fused_setup([(i, k) for i, k in enumerate(range(E, D))])
+    assert fz is not None and fz['ns'] == (6 if mixed else 3) and (fz['R'] is not None) == (E > 0)
+    got = tm.inverse_map(Z.copy(), xs())
+    assert rel_err(got, om.inverse_map(Z.copy(), xs())) <= 1e-10
+    monkeypatch.setenv('TTM_INV_SPLIT', '0')                   # the one-launch walk: same numbers up to summation order
+    assert tm._inverse_fused_setup([(i, k) for i, k in enumerate(range(E, D))])['R'] is None
+    assert rel_err(tm.inverse_map(Z.copy(), xs()), got) <= 1e-12
+
+
 @pytest.mark.parametrize('name', ['sep_ex05', 'sep_ex06_cycle', 'sep_c5_d6'])
 def test_per_component_paths_match_the_fused_ones(name, monkeypatch):
     """map / inverse_map / densities through the per-component kernels (TTM_MAP_FUSED=0, TTM_INV_FUSED=0: the paths

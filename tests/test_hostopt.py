@@ -54,3 +54,35 @@ def test_reports_line_search_failure_like_scipy():
     ref = minimize(f, x0, jac=g, method='BFGS')
     res = H.quasi_newton(lambda x: (f(x), g(x)), x0)
     assert res.status == ref.status
+
+
+def test_lbfgsb_lockstep_reproduces_scipy_per_problem():
+    """Several bounded problems of different size and iteration count advanced together: every one must end on
+    scipy.optimize.minimize(method='L-BFGS-B')'s iterate, bit for bit, with the same nit / nfev / status."""
+    from scipy.optimize import minimize
+    hostopt = H
+    assert hostopt.lbfgsb_available()
+    rng = np.random.default_rng(5)
+    probs = []
+    for n in (1, 3, 6, 11):
+        Q = rng.standard_normal((n, n))
+        Q = Q @ Q.T / n + 0.1 * np.eye(n)
+        c = rng.standard_normal(n)
+
+        def fg(x, Q=Q, c=c):                       # the separable fits' shape: quadratic minus log of a positive sum
+            s = 1e-3 + np.sum(x) + 0.5
+            return 0.5 * x @ Q @ x + c @ x - np.log(s), Q @ x + c - 1.0 / s
+        lb = np.zeros(n)
+        ub = np.full(n, np.inf)
+        if n > 2:
+            ub[1] = 0.25
+        probs.append((fg, rng.uniform(0.1, 1.0, n), lb, ub))
+    box = {}
+    res = hostopt.lbfgsb_lockstep([p[1] for p in probs], [(p[2], p[3]) for p in probs],
+                                  lambda i, x: box.__setitem__(i, probs[i][0](x.copy())), lambda i: box.pop(i))
+    for (fg, x0, lb, ub), mine in zip(probs, res):
+        ref = minimize(fg, x0, jac=True, method='L-BFGS-B',
+                       bounds=[(l, None if np.isinf(u) else u) for l, u in zip(lb, ub)])
+        assert np.array_equal(ref.x, mine.x)
+        assert (ref.nit, ref.nfev, ref.status, ref.fun) == (mine.nit, mine.nfev, mine.status, mine.fun)
+        assert ref.message == mine.message

@@ -37,14 +37,30 @@ g = torch.Generator(device='cuda').manual_seed(0)
 Xw = torch.zeros(D, n, dtype=torch.float64, device='cuda')
 Xw[:E] = torch.randn(E, n, dtype=torch.float64, device='cuda', generator=g)
 Zt = torch.randn(D - E, n, dtype=torch.float64, device='cuda', generator=g)
-ts = []
-for rep in range(4):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    tm._inverse_fused_launch(fused, Xw, n, n, Zt, n)
-    e1.record()
-    torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1) * 1e-3)
+def timed(fz):
+    base = torch.empty(D - E, (n + 1) // 2 * 2, dtype=torch.float64, device='cuda') if fz.get('R') is not None else None
+    ts = []
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tm._inverse_fused_launch(fz, Xw, n, n, Zt, n, base=base)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return ts
+
+
+# one launch (walk over every column) vs K-inv-rect + walk over the solved columns
+os.environ['TTM_INV_SPLIT'] = '0'
+f_single = tm._inverse_fused_setup(comps)
+ts = timed(f_single)
+out['single_s'] = min(ts[1:])
+X_single = Xw[E:].clone()
+os.environ['TTM_INV_SPLIT'] = 'auto'
+fused = tm._inverse_fused_setup(comps)
+out['split'] = fused.get('R') is not None
+ts = timed(fused)
+out['split_vs_single_maxabs'] = float((Xw[E:] - X_single).abs().max())
 out['fused_s'] = min(ts[1:])
 out['fused_samples_per_s'] = n / out['fused_s']
 out['algorithmic_bytes'] = 8 * n * (E + 2 * (D - E))

@@ -63,11 +63,16 @@ def lib():
             'ttm_gram': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p],
             'ttm_gram_tail': [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p],
             'ttm_sep_objgrad': [c_void_p, c_void_p, c_int64, c_int64, _dp, _dp, c_void_p],
+            'ttm_sep_objgrad_launch': [c_void_p, c_void_p, c_int64, c_int64, _dp, c_void_p],
+            'ttm_sep_objgrad_wait': [c_void_p, _dp, c_void_p],
             'ttm_mon_table': [c_void_p, c_int, c_void_p, c_void_p],
             'ttm_inverse_table': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p],
             'ttm_inverse_fused_apack_size': [c_int, c_int, c_int, ctypes.POINTER(c_int64)],
             'ttm_inverse_fused': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_int, c_int, c_void_p],
+            'ttm_inverse_rect_rpack_size': [c_int, c_int, c_int, ctypes.POINTER(c_int64)],
+            'ttm_inverse_fused_split': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p],
             'ttm_inverse_bisect': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,
                                    ctypes.POINTER(c_int), c_void_p],
             'ttm_density_accumulate': [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int64, c_void_p],

@@ -487,15 +487,14 @@ int ttm_gram_tail(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, int firs
     return TTM_OK;
 }
 
-int ttm_sep_objgrad(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* host_b, double* host_out,
-                    void* stream) {
-    if (!p || !Xt || !host_b || !host_out || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: bad arguments");
+int ttm_sep_objgrad_launch(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* host_b, void* stream) {
+    if (!p || !Xt || !host_b || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: bad arguments");
     CK(cudaSetDevice(p->ctx->device));
     const int mm = p->view.m_dmon;
     if (mm > p->m) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: inconsistent plan");
     // the coefficients are read by the kernel straight from pinned (mapped) host memory and the result comes back
-    // the same way: one launch, no copies, no stream synchronisation (the call returns after the result arrived, so
-    // h_pin is free again)
+    // the same way: one launch, no copies, no stream synchronisation (h_pin is free again once the result arrived;
+    // callers of the split form collect every launch with ttm_sep_objgrad_wait before launching on the plan again)
     CK(cudaEventSynchronize(p->ev_h2d));
     std::memcpy(p->h_pin, host_b, mm * sizeof(double));
     double* d_b = p->d_coeffs + p->view.m_non;
@@ -505,7 +504,20 @@ int ttm_sep_objgrad(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const 
                                       (cudaStream_t)stream);
     if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_sep_objgrad: too many monotone terms for shared memory");
     CK(e);
-    return wait_result(p, host_out, 1 + mm, (cudaStream_t)stream);
+    return TTM_OK;
+}
+
+int ttm_sep_objgrad_wait(ttm_plan* p, double* host_out, void* stream) {
+    if (!p || !host_out) return fail(TTM_ERR_ARG, "ttm_sep_objgrad_wait: bad arguments");
+    return wait_result(p, host_out, 1 + p->view.m_dmon, (cudaStream_t)stream);
+}
+
+int ttm_sep_objgrad(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* host_b, double* host_out,
+                    void* stream) {
+    if (!host_out) return fail(TTM_ERR_ARG, "ttm_sep_objgrad: bad arguments");
+    int rc = ttm_sep_objgrad_launch(p, Xt, ld, N, host_b, stream);
+    if (rc) return rc;
+    return ttm_sep_objgrad_wait(p, host_out, stream);
 }
 
 int ttm_mon_table(ttm_plan* p, int ntab, double* table, void* stream) {
@@ -555,6 +567,34 @@ int ttm_inverse_fused(ttm_ctx* c, double* Xw, int64_t ld, int64_t N, const doubl
     InvFusedArgs a;
     a.Xw = Xw; a.ld = ld; a.N = N; a.Zt = Zt; a.ldz = ldz; a.ncomp = ncomp; a.c0 = c0; a.ns = ns;
     a.Apack = Apack; a.a0 = a0; a.tables = tables; a.ntab = ntab; a.truncate = truncate;
+    a.base = nullptr; a.ldb = 0;
+    CK(ttm_launch_inverse_fused(a, c->sm_count, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_inverse_rect_rpack_size(int ncomp, int c0, int ns, int64_t* host_doubles) {
+    if (ncomp <= 0 || c0 < 0 || (ns != 3 && ns != 6) || !host_doubles) return fail(TTM_ERR_ARG, "ttm_inverse_rect_rpack_size: bad arguments");
+    *host_doubles = (int64_t)ttm_inverse_rect_rpack_doubles(ncomp, c0, ns);
+    return TTM_OK;
+}
+
+int ttm_inverse_fused_split(ttm_ctx* c, double* Xw, int64_t ld, int64_t N, const double* Zt, int64_t ldz, int ncomp, int c0,
+                            int ns, const double* Apack, const double* Rpack, const double* a0, const double* tables,
+                            int ntab, int truncate, double* base, int64_t ldb, void* stream) {
+    if (!c || !Xw || !Zt || !Apack || !Rpack || !a0 || !tables || !base || N <= 0 || ld < N || ldz < N || ldb < N ||
+        ncomp <= 0 || c0 <= 0 || ntab < 2)
+        return fail(TTM_ERR_ARG, "ttm_inverse_fused_split: bad arguments");
+    if (ns != 3 && ns != 6) return fail(TTM_ERR_ARG, "ttm_inverse_fused_split: ns must be 3 or 6");
+    if ((ldb & 1) || (reinterpret_cast<uintptr_t>(base) & 15))
+        return fail(TTM_ERR_ARG, "ttm_inverse_fused_split: base must be 16-byte aligned with an even leading dimension");
+    CK(cudaSetDevice(c->device));
+    InvRectArgs r;
+    r.Xw = Xw; r.ld = ld; r.N = N; r.ncomp = ncomp; r.c0 = c0; r.ns = ns; r.Rpack = Rpack; r.base = base; r.ldb = ldb;
+    CK(ttm_launch_inverse_rect(r, c->sm_count, (cudaStream_t)stream));
+    InvFusedArgs a;
+    a.Xw = Xw; a.ld = ld; a.N = N; a.Zt = Zt; a.ldz = ldz; a.ncomp = ncomp; a.c0 = c0; a.ns = ns;
+    a.Apack = Apack; a.a0 = a0; a.tables = tables; a.ntab = ntab; a.truncate = truncate;
+    a.base = base; a.ldb = ldb;
     CK(ttm_launch_inverse_fused(a, c->sm_count, (cudaStream_t)stream));
     return TTM_OK;
 }

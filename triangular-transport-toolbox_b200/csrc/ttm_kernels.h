@@ -137,7 +137,20 @@ struct InvFusedArgs {
     const double* a0;      // [ncomp] constant part of the offset
     const double* tables;  // [ncomp][2*ntab] sorted values | abscissae
     int ntab, truncate;
+    const double* base;    // NULL, or [ncomp][ldb]: offsets' share of the columns < c0 (K-inv-rect); the walk then starts at c0
+    int64_t ldb;
 };
+// K-inv-rect: base[j][i] = sum_{v<c0} sum_q f_q(Xw[v][i]) Rpack[j/128][v][q][j%128]
+struct InvRectArgs {
+    const double* Xw;
+    int64_t ld, N;
+    int ncomp, c0, ns;
+    const double* Rpack;   // [ceil(ncomp/128)][c0 rounded up to 8][ns][128], zero padded
+    double* base;          // [ncomp][ldb], 16-byte aligned, ldb even
+    int64_t ldb;
+};
+cudaError_t ttm_launch_inverse_rect(const InvRectArgs& a, int sm_count, cudaStream_t st);
+size_t ttm_inverse_rect_rpack_doubles(int ncomp, int c0, int ns);
 cudaError_t ttm_launch_inverse_fused(const InvFusedArgs& a, int sm_count, cudaStream_t st);
 size_t ttm_inverse_fused_apack_doubles(int ncomp, int c0, int ns);
 

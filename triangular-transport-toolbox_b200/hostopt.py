@@ -90,3 +90,143 @@ def quasi_newton(fg, x0, gtol=1e-5, c1=1e-4, c2=0.9, maxiter=None):
     elif status == 0 and (np.isnan(gnorm) or np.isnan(f_old) or np.isnan(x).any()):
         status = 3
     return Result(x=x, fun=f_old, jac=g, nit=it, nfev=last['nfev'], status=status, success=(status == 0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# L-BFGS-B for the separable fits, all components in lockstep
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference fits the components of a separable map with `minimize(method='L-BFGS-B', jac=True, bounds=...)`, one
+# process per component (tm.py:2837-2845, :3101-3107).  scipy's L-BFGS-B is a reverse-communication routine
+# (`_lbfgsb.setulb`: "give me f and g at x" / "new iteration" / "done"), so K independent minimisations can be advanced
+# together: every round launches the objective kernels of all components that asked for (f, g), then collects them.
+# The number of host<->GPU round trips drops from sum_k nfev_k to max_k nfev_k, and the kernels of one round queue
+# back to back.  The iterates are scipy's own: the routine, its workspace layout and the stopping logic around it
+# (factr = ftol/eps, pgtol, maxls = 20, maxiter = maxfun = 15000) follow scipy.optimize._lbfgsb_py._minimize_lbfgsb of
+# the installed scipy; `lbfgsb_available()` checks once that this driver reproduces `minimize` bit for bit on a small
+# bounded problem and otherwise the class keeps calling `minimize` per component.
+
+try:
+    from scipy.optimize import _lbfgsb as _lb
+    from scipy.optimize._lbfgsb_py import status_messages as _lb_status, task_messages as _lb_task
+except Exception:                                        # pragma: no cover
+    _lb = None
+
+_LB_OK = None
+
+
+class _LbState:
+    def __init__(self, x0, lb, ub, m=10):
+        n = x0.size
+        try:
+            from scipy.optimize._lbfgsb_py import HAS_ILP64
+        except Exception:                                # pragma: no cover
+            HAS_ILP64 = False
+        it = np.int64 if HAS_ILP64 else np.int32
+        self.n, self.m = n, m
+        self.low = np.zeros(n)
+        self.up = np.zeros(n)
+        self.nbd = np.zeros(n, dtype=it)
+        for i in range(n):
+            hl, hu = np.isfinite(lb[i]), np.isfinite(ub[i])
+            if hl:
+                self.low[i] = lb[i]
+            if hu:
+                self.up[i] = ub[i]
+            self.nbd[i] = (2 if hu else 1) if hl else (3 if hu else 0)
+        self.x = np.clip(np.array(x0, dtype=np.float64), lb, ub)
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros(n)
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m)
+        self.iwa = np.zeros(3 * n, dtype=it)
+        self.task = np.zeros(2, dtype=it)
+        self.ln_task = np.zeros(2, dtype=it)
+        self.lsave = np.zeros(4, dtype=it)
+        self.isave = np.zeros(44, dtype=it)
+        self.dsave = np.zeros(29)
+        self.nit = 0
+        self.nfev = 0
+        self.done = False
+
+
+def _lb_advance(s, factr, pgtol, maxls, maxiter, maxfun):
+    """Run setulb until it wants (f, g) at s.x (returns True) or stops (returns False)."""
+    while True:
+        _lb.setulb(s.m, s.x, s.low, s.up, s.nbd, s.f, s.g, factr, pgtol, s.wa, s.iwa, s.task, s.lsave, s.isave,
+                   s.dsave, maxls, s.ln_task)
+        if s.task[0] == 3:
+            return True
+        if s.task[0] == 1:
+            s.nit += 1
+            if s.nit >= maxiter:
+                s.task[0], s.task[1] = 5, 504
+            elif s.nfev > maxfun:
+                s.task[0], s.task[1] = 5, 502
+        else:
+            s.done = True
+            return False
+
+
+def lbfgsb_lockstep(x0s, bounds, launch, collect, ftol=2.2204460492503131e-09, gtol=1e-5, maxls=20, maxiter=15000,
+                    maxfun=15000):
+    """Minimise len(x0s) independent bound-constrained problems with scipy's L-BFGS-B core, in lockstep.
+    bounds[i] = (lb, ub) arrays (+-inf for none); launch(i, x) starts the evaluation of problem i at x (x is only
+    valid during the call), collect(i) -> (f, grad) finishes it.  Returns one Result per problem."""
+    factr = ftol / np.finfo(float).eps
+    states = [_LbState(np.asarray(x0, dtype=np.float64).ravel(), np.asarray(b[0], dtype=np.float64),
+                       np.asarray(b[1], dtype=np.float64)) for x0, b in zip(x0s, bounds)]
+    active = list(range(len(states)))
+    while active:
+        want = [i for i in active if _lb_advance(states[i], factr, gtol, maxls, maxiter, maxfun)]
+        for i in want:
+            launch(i, states[i].x)
+        for i in want:
+            f, g = collect(i)
+            s = states[i]
+            s.f = float(f)
+            s.g = np.asarray(g, dtype=np.float64)
+            s.nfev += 1
+        active = want
+    out = []
+    for s in states:
+        if s.task[0] == 4:
+            flag = 0
+        elif s.nfev > maxfun or s.nit >= maxiter:
+            flag = 1
+        else:
+            flag = 2
+        out.append(Result(x=s.x, fun=float(s.f), jac=s.g, nit=s.nit, nfev=s.nfev, status=flag, success=(flag == 0),
+                          message=_lb_status[int(s.task[0])] + ": " + _lb_task[int(s.task[1])]))
+    return out
+
+
+def lbfgsb_available():
+    """True when the lockstep driver reproduces scipy.optimize.minimize(method='L-BFGS-B') exactly (checked once on a
+    5-variable bounded problem); False when scipy's private routine is missing or has another calling convention."""
+    global _LB_OK
+    if _LB_OK is None:
+        _LB_OK = False
+        if _lb is not None:
+            try:
+                from scipy.optimize import minimize
+
+                def fg(x):
+                    r = x[1:] - x[:-1] ** 2
+                    f = float(np.sum(100.0 * r ** 2 + (1 - x[:-1]) ** 2))
+                    g = np.zeros_like(x)
+                    g[:-1] = -400.0 * x[:-1] * r - 2 * (1 - x[:-1])
+                    g[1:] += 200.0 * r
+                    return f, g
+                x0 = np.array([-1.2, 1.0, 0.7, -0.3, 1.9])
+                lb = np.array([-2.0, -np.inf, 0.5, -1.0, -np.inf])
+                ub = np.array([0.8, np.inf, np.inf, 0.9, 2.0])
+                ref = minimize(fg, x0, jac=True, method='L-BFGS-B',
+                               bounds=[(l if np.isfinite(l) else None, u if np.isfinite(u) else None)
+                                       for l, u in zip(lb, ub)])
+                box = {}
+                mine = lbfgsb_lockstep([x0], [(lb, ub)], lambda i, x: box.__setitem__(i, fg(x.copy())),
+                                       lambda i: box[i])[0]
+                _LB_OK = bool(np.array_equal(ref.x, mine.x) and ref.nit == mine.nit and ref.nfev == mine.nfev
+                              and ref.fun == mine.fun and ref.status == mine.status)
+            except Exception:
+                _LB_OK = False
+    return _LB_OK

@@ -22,6 +22,7 @@ import os
 import numpy as np
 
 from . import binding as B
+from . import hostopt
 from .plan import ComponentPlan, resolve_family
 
 _RECT = {'exponential': 0, 'softplus': 1, 'squared': 2, 'expneg': 3, 'explinearunit': 4}
@@ -888,6 +889,52 @@ class transport_map():
                              'success': bool(opt.success)}
         return (back(opt.x), opt.x)
 
+    def _fit_separable_lockstep(self, comps):
+        """Separable fits of the listed components (tm.py:2903-3172 per component), their L-BFGS-B iterations advanced
+        together: every round launches K-sepobj for each component that asked for (f, g) and then collects the
+        results (hostopt.lbfgsb_lockstep; the iterates are those of scipy's minimize).  With a sample-sharded
+        ensemble every rank runs the same iteration on all-reduced sums."""
+        setups, x0s, bnds = {}, [], []
+        for k in comps:
+            if self._host_plans[k].m_non == 0:
+                raise ValueError("separable monotonicity requires at least one nonmonotone term per component "
+                                 "(the reference's np.linalg.qr(None) fails too)")
+            A, back = self._separable_setup(k)
+            setups[k] = (A, back, self.delta * np.sum(A, axis=-1))
+            x0s.append(np.array(self.coeffs_mon[k], dtype=np.float64))
+            inf = lambda v, sgn: sgn * np.inf if v is None else float(v)
+            bnds.append((np.array([inf(v, -1.0) for v in self.optimization_constraints_lb[k]]),
+                         np.array([inf(v, 1.0) for v in self.optimization_constraints_ub[k]])))
+        lib, Xp, ld, N, st = self._lib, B.c_void_p(self._Xt.data_ptr()), self._Xt.shape[1], self._N, self._stream()
+        outs = [np.empty(1 + self._host_plans[k].m_dmon) for k in comps]
+        held = {}
+
+        def launch(i, b):
+            held[i] = np.array(b, dtype=np.float64)                  # setulb updates its x in place
+            B.check(lib.ttm_sep_objgrad_launch(self._plans[comps[i]], Xp, ld, N, B.dptr(held[i]), st))
+
+        def collect(i):
+            k = comps[i]
+            B.check(lib.ttm_sep_objgrad_wait(self._plans[k], B.dptr(outs[i]), st))
+            out = outs[i]
+            if self._sharded:
+                from .parallel import allreduce_sum
+                out = allreduce_sum(out, self._device)
+            A, _, bvec = setups[k]
+            b = held[i]
+            Ax = A @ b
+            Ng = self._N_global
+            return b @ Ax / 2 - out[0] / Ng + b @ bvec, Ax - out[1:] / Ng + bvec
+
+        res = hostopt.lbfgsb_lockstep(x0s, bnds, launch, collect)
+        results = {}
+        for k, opt in zip(comps, res):
+            self._last_opt = opt
+            self._fit_info[k] = {'nit': int(opt.nit), 'nfev': int(opt.nfev), 'fun': float(opt.fun),
+                                 'success': bool(opt.success)}
+            results[k] = (setups[k][1](opt.x), opt.x)
+        return results
+
     def optimize(self, K=None):
         """tm.py:2714-2901.  Components are independent; with torch.distributed initialised they are sharded
         over the ranks (longest first, like the reference's Pool over np.flip(K)) and the coefficients are
@@ -928,6 +975,9 @@ class transport_map():
             finally:
                 B.check(self._lib.ttm_ctx_set_blocks_per_sm(self._ctx, 0))
             torch.cuda.synchronize(self._device)
+        elif (self.monotonicity != "integrated rectifier" and len(mine) > 0
+              and os.environ.get('TTM_HOST_OPT', '') != 'scipy' and hostopt.lbfgsb_available()):
+            results = self._fit_separable_lockstep(mine)
         else:
             for k in mine:
                 results[k] = fit(k, None)
@@ -1036,7 +1086,8 @@ class transport_map():
         for k in ks:
             h.update(np.ascontiguousarray(self.coeffs_nonmon[k], dtype=np.float64).tobytes())
             h.update(np.ascontiguousarray(self.coeffs_mon[k], dtype=np.float64).tobytes())
-        key = (tuple(ks), resolution, self._ensemble_version, h.digest())
+        mode = os.environ.get('TTM_INV_SPLIT', 'auto')
+        key = (tuple(ks), resolution, self._ensemble_version, h.digest(), mode)
         hit = getattr(self, '_inv_fused_cache', None)
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -1058,6 +1109,12 @@ class transport_map():
         B.check(self._lib.ttm_inverse_fused_apack_size(ncomp, c0, ns, B.ctypes.byref(size)))
         A = np.zeros(size.value)
         a0 = np.zeros(ncomp)
+        # wide conditioning block: its share of the offsets is one GEMM (K-inv-rect) ahead of the sequential walk
+        split = c0 > 0 and mode != '0' and (mode == '1' or (c0 >= 32 and ncomp >= 32))
+        c0p = (c0 + 7) // 8 * 8
+        if split:
+            B.check(self._lib.ttm_inverse_rect_rpack_size(ncomp, c0, ns, B.ctypes.byref(size)))
+            R = np.zeros(size.value)
         cache = self.__dict__.setdefault('_inv_pack_cache', {})
         for j, (k, p) in enumerate(zip(ks, plans)):
             cn = np.asarray(self.coeffs_nonmon[k], dtype=np.float64)
@@ -1066,7 +1123,7 @@ class transport_map():
             if key not in cache:                                           # static part of the packing, per component
                 b, jj = divmod(j, CB)
                 row0 = b * (c0 + CB) + CB * b * (b - 1) // 2
-                dst, src, sc = [], [], []
+                dst, src, sc, rdst = [], [], [], []
                 for v, idx_row, sc_row in p.dense_groups:
                     if v >= c0 + j:
                         cache[key] = None                                  # not a triangular dependency
@@ -1076,18 +1133,35 @@ class transport_map():
                             dst.append(((row0 + v) * CB + jj) * ns + q)
                             src.append(int(idx_row[sl]))
                             sc.append(float(sc_row[sl]))
+                            # K-inv-rect operand [j // 128][v][slot][j % 128]; -1: a column the walk itself solves
+                            rdst.append((((j // 128) * c0p + v) * ns + q) * 128 + j % 128 if v < c0 else -1)
                 else:
-                    cache[key] = (np.asarray(dst, dtype=np.int64), np.asarray(src, dtype=np.int64), np.asarray(sc))
+                    cache[key] = (np.asarray(dst, dtype=np.int64), np.asarray(src, dtype=np.int64), np.asarray(sc),
+                                  np.asarray(rdst, dtype=np.int64))
             if cache[key] is None:
                 return None
-            dst, src, sc = cache[key]
+            dst, src, sc, rdst = cache[key]
             A[dst] = cn[src] * sc
+            if split:
+                keep = rdst >= 0
+                R[rdst[keep]] = (cn[src] * sc)[keep]
         fused = {'ncomp': ncomp, 'c0': c0, 'ns': ns, 'A': self._upload(A), 'a0': self._upload(a0),
-                 'tabs': self._monotone_tables(comps, resolution=resolution), 'ntab': resolution}
+                 'tabs': self._monotone_tables(comps, resolution=resolution), 'ntab': resolution,
+                 'R': self._upload(R) if split else None}
         self._inv_fused_cache = (key, fused)
         return fused
 
-    def _inverse_fused_launch(self, f, Xw, ld, n, Zt, ldz, stream=None):
+    def _inverse_fused_launch(self, f, Xw, ld, n, Zt, ldz, stream=None, base=None):
+        if f.get('R') is not None:
+            # two launches: K-inv-rect (conditioning block -> base), then the walk over the solved columns
+            if base is None:
+                base = self._torch.empty((f['ncomp'], (n + 1) // 2 * 2), dtype=self._torch.float64, device=self._device)
+            B.check(self._lib.ttm_inverse_fused_split(
+                self._ctx, B.c_void_p(Xw.data_ptr()), ld, n, B.c_void_p(Zt.data_ptr()), ldz, f['ncomp'], f['c0'], f['ns'],
+                B.c_void_p(f['A'].data_ptr()), B.c_void_p(f['R'].data_ptr()), B.c_void_p(f['a0'].data_ptr()),
+                B.c_void_p(f['tabs'].data_ptr()), f['ntab'], 1 if self.root_search_truncation else 0,
+                B.c_void_p(base.data_ptr()), base.shape[1], stream if stream is not None else self._stream()))
+            return
         B.check(self._lib.ttm_inverse_fused(self._ctx, B.c_void_p(Xw.data_ptr()), ld, n, B.c_void_p(Zt.data_ptr()), ldz,
                                             f['ncomp'], f['c0'], f['ns'], B.c_void_p(f['A'].data_ptr()),
                                             B.c_void_p(f['a0'].data_ptr()), B.c_void_p(f['tabs'].data_ptr()), f['ntab'],
@@ -1149,6 +1223,8 @@ class transport_map():
                 'dx': torch.empty((cap, E), dtype=f64, device=dev) if E > 0 else None,
                 'Xw': torch.empty((ncol, cap), dtype=f64, device=dev),
                 'Zt': torch.empty((nz, cap), dtype=f64, device=dev),
+                'base': (torch.empty((nz, (cap + 1) // 2 * 2), dtype=f64, device=dev)
+                         if fused is not None and fused.get('R') is not None else None),
                 'out': torch.empty((cap, nout), dtype=f64, device=dev)})
         out_host = torch.empty((N, nout), dtype=f64, pin_memory=True)
         trunc = 1 if self.root_search_truncation else 0
@@ -1196,7 +1272,7 @@ class transport_map():
                         B.check(lib.ttm_standardize_transpose(self._ctx, ptr(sl['dx']), n, E, ptr(mean_in), ptr(std_in),
                                                               ptr(sl['Xw']), cap, st))
                     if fused is not None:
-                        self._inverse_fused_launch(fused, sl['Xw'], cap, n, sl['Zt'], cap, stream=st)
+                        self._inverse_fused_launch(fused, sl['Xw'], cap, n, sl['Zt'], cap, stream=st, base=sl['base'])
                     for (i, k), tab in zip(comps, tabs):
                         B.check(lib.ttm_inverse_table(self._plans[k], ptr(sl['Xw']), cap, n,
                                                       B.c_void_p(sl['Zt'].data_ptr() + i * cap * 8), ptr(tab),
