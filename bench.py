@@ -248,12 +248,28 @@ def inverse_metric(rank, world, dist, torch, with_cpu=False):
         alg_bytes = 8 * ns * (E + 2 * (Dm - E))                         # X* in, Z in, X out
         pairs = sum(k for k in range(E, Dm))                            # (variable, component) pairs per sample
         fl = ns * (2 * 3 * pairs + 30 * (Dm - E))                       # 3 FMA per pair + interpolation
+        peak64 = None
+        traffic = None
+        try:
+            peak64 = json.load(open(os.path.join(ROOT, 'profiles', 'fp64_peaks_r2.json'))).get('dfma_tflops')
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_inverse_traffic_r2.json')))
+            traffic = tr['bytes_per_sample_split'] * ns if fused.get('R') is not None else None
+        except Exception:
+            pass
         dev = {'samples_per_s': ns * world / t_dev, 'seconds': t_dev,
-               'roofline': {'bound': 'fp64', 'achieved': fl / t_dev / 1e12, 'unit': 'TFLOP/s',
+               'kernels': ['inverse_rect_kernel (DMMA GEMM over the conditioning block)', 'inverse_fused_kernel (walk)']
+               if fused.get('R') is not None else ['inverse_fused_kernel'],
+               'roofline': {'bound': 'fp64', 'achieved': fl / t_dev / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
+                            'frac': (fl / t_dev / 1e12 / peak64) if peak64 else None,
                             'flops_per_sample': fl / ns, 'algorithmic_bytes': alg_bytes,
-                            'algorithmic_gbs': alg_bytes / t_dev / 1e9,
-                            'how': 'K-inv-fused, inputs resident in HBM, CUDA events; flops = 3 FMA per (sample, variable, '
-                                   'component) pair of the triangular contraction (exp of the features not counted)'}}
+                            'algorithmic_gbs': alg_bytes / t_dev / 1e9, 'traffic': traffic,
+                            'traffic_ratio': (traffic / alg_bytes) if traffic else None,
+                            'traffic_source': 'profiles/ncu_inverse_traffic_r2.json (ncu dram bytes of both kernels, scaled '
+                                              'per sample)',
+                            'how': 'conditional inverse, inputs resident in HBM, CUDA events over both launches; flops = 3 '
+                                   'FMA per (sample, variable, component) pair of the triangular contraction (exp of the '
+                                   'features, table search and interpolation not counted)'}}
+        del base
         del Xw, Zt
     cpu = None
     parity = None

@@ -171,6 +171,15 @@ int ttm_sep_objgrad(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, con
  * per plan may be outstanding. */
 int ttm_sep_objgrad_launch(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, const double* host_b, void* stream);
 int ttm_sep_objgrad_wait(ttm_plan* plan, double* host_out, void* stream);
+/* fun_mon_objective (tm.py:2978-3006) whole, for n components in one call: every K-sepobj launch is queued, then each
+ * result is collected and the reduced objective assembled on the host,
+ *   fg[i][0]   = b^T A b / 2 - (sum_s log dS_s) / n_total + b^T c,
+ *   fg[i][1+j] = (A b)_j - (sum_s dPsi_sj / dS_s) / n_total + c_j,
+ * with A = host_A[i] (m_mon x m_mon, row-major, symmetric), c = host_c[i] = delta * rowsum(A), b = host_b[i].
+ * n_total = number of samples of the whole ensemble.  A plan may appear once per call. */
+int ttm_sep_reduced_batch(int n, ttm_plan* const* plans, const double* Xt, int64_t ld, int64_t N, double n_total,
+                          const double* const* host_b, const double* const* host_A, const double* const* host_c,
+                          double* const* host_fg, void* stream);
 
 /* ---- K-inv -----------------------------------------------------------------------------------
  * replaces: vectorized_root_search_alternate tm.py:3987-4084 (table) and

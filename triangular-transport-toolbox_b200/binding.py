@@ -65,6 +65,9 @@ def lib():
             'ttm_sep_objgrad': [c_void_p, c_void_p, c_int64, c_int64, _dp, _dp, c_void_p],
             'ttm_sep_objgrad_launch': [c_void_p, c_void_p, c_int64, c_int64, _dp, c_void_p],
             'ttm_sep_objgrad_wait': [c_void_p, _dp, c_void_p],
+            'ttm_sep_reduced_batch': [c_int, ctypes.POINTER(c_void_p), c_void_p, c_int64, c_int64, ctypes.c_double,
+                                      ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                      ctypes.POINTER(c_void_p), c_void_p],
             'ttm_mon_table': [c_void_p, c_int, c_void_p, c_void_p],
             'ttm_inverse_table': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p],
             'ttm_inverse_fused_apack_size': [c_int, c_int, c_int, ctypes.POINTER(c_int64)],

@@ -50,6 +50,9 @@ struct ttm_ctx {
     FusedComp* h_fused = nullptr;
     int fused_cap = 0;
     cudaEvent_t ev_fused = nullptr;
+    static constexpr int NSIDE = 8;  // side streams of ttm_sep_reduced_batch (independent components overlap)
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t ev_side = nullptr;
 };
 
 struct ttm_plan {
@@ -119,6 +122,8 @@ int ttm_ctx_destroy(ttm_ctx* c) {
     cudaFree(c->d_fused);
     if (c->h_fused) cudaFreeHost(c->h_fused);
     if (c->ev_fused) cudaEventDestroy(c->ev_fused);
+    for (cudaStream_t q : c->side) if (q) cudaStreamDestroy(q);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
     delete c;
     return TTM_OK;
 }
@@ -510,6 +515,62 @@ int ttm_sep_objgrad_launch(ttm_plan* p, const double* Xt, int64_t ld, int64_t N,
 int ttm_sep_objgrad_wait(ttm_plan* p, double* host_out, void* stream) {
     if (!p || !host_out) return fail(TTM_ERR_ARG, "ttm_sep_objgrad_wait: bad arguments");
     return wait_result(p, host_out, 1 + p->view.m_dmon, (cudaStream_t)stream);
+}
+
+int ttm_sep_reduced_batch(int n, ttm_plan* const* plans, const double* Xt, int64_t ld, int64_t N, double n_total,
+                          const double* const* host_b, const double* const* host_A, const double* const* host_c,
+                          double* const* host_fg, void* stream) {
+    if (n < 0 || (n > 0 && (!plans || !host_b || !host_A || !host_c || !host_fg)) || !(n_total > 0.0))
+        return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!plans[i] || !host_b[i] || !host_A[i] || !host_c[i] || !host_fg[i])
+            return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: null entry");
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (plans[i] == plans[j]) return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: a plan may appear once per call");
+    // all launches first.  The components are independent: with more than one they go to side streams ordered after
+    // the caller's stream, so that the (small, latency-bound) kernels overlap instead of queueing.  Completion is
+    // observed by the host through each plan's result mirror, so nothing has to be joined back.
+    ttm_ctx* c = n > 0 ? plans[0]->ctx : nullptr;
+    const bool fan = n > 1;
+    if (fan) {
+        CK(cudaSetDevice(c->device));
+        if (!c->ev_side) CK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+        CK(cudaEventRecord(c->ev_side, (cudaStream_t)stream));
+    }
+    auto lane = [&](int i) -> cudaStream_t {
+        if (!fan) return (cudaStream_t)stream;
+        return c->side[i % ttm_ctx::NSIDE];
+    };
+    for (int i = 0; i < n; ++i) {
+        if (plans[i]->ctx != c) return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: plans of different contexts");
+        if (fan) {
+            cudaStream_t& q = c->side[i % ttm_ctx::NSIDE];
+            if (!q) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            if (i < ttm_ctx::NSIDE) CK(cudaStreamWaitEvent(q, c->ev_side, 0));
+        }
+        int rc = ttm_sep_objgrad_launch(plans[i], Xt, ld, N, host_b[i], lane(i));
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n; ++i) {                       // then collect; the m x m algebra runs while the others finish
+        ttm_plan* p = plans[i];
+        const int m = p->view.m_dmon;
+        double* fg = host_fg[i];
+        int rc = wait_result(p, fg, 1 + m, lane(i));
+        if (rc) return rc;
+        const double *b = host_b[i], *A = host_A[i], *c = host_c[i];
+        double quad = 0.0, lin = 0.0;
+        const double sumlog = fg[0];
+        for (int r = 0; r < m; ++r) {
+            double ab = 0.0;
+            for (int q = 0; q < m; ++q) ab += A[(size_t)r * m + q] * b[q];
+            quad += b[r] * ab;
+            lin += b[r] * c[r];
+            fg[1 + r] = ab - fg[1 + r] / n_total + c[r];
+        }
+        fg[0] = quad / 2 - sumlog / n_total + lin;
+    }
+    return TTM_OK;
 }
 
 int ttm_sep_objgrad(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* host_b, double* host_out,

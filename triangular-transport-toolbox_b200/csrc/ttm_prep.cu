@@ -130,19 +130,27 @@ __global__ void __launch_bounds__(T_BAS) basis_kernel(const PlanView P, int o_pt
 // transpose tile in 128-byte pieces.  HBM-bound when writing: 8 N (k+1) read + 8 N m written.
 constexpr int BD_MAXORD = 1 << 20;   // no limit: the ladder is a two-term state
 
+// FAM: compile-time polynomial family (the recurrence coefficients fold into the ladder), -1: read P.family.
+// blockIdx.y selects a window of BD_WIN consecutive terms, so that short ensembles still fill the machine (a thread
+// walking all m terms of its sample left 1.3 waves of blocks at n = 2e5, m = 766); the ladder restarts per window.
+constexpr int BD_WIN = 12 * TJ_BAS;
+
+template <int FAM>
 __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
                                                             int64_t N, double* __restrict__ Psi, int64_t ldp, int coff) {
     __shared__ double tile[TJ_BAS][T_BAS + 1];
-    extern __shared__ double s_dyn[];            // per term: scale [m] | packed {column : 20, order : 10, hf : 1, valid : 1} [m]
-    const int m = P.m_non;
+    extern __shared__ double s_dyn[];            // per term of the window: scale | packed {column : 20, order : 10, hf : 1, valid : 1}
+    const int family = FAM >= 0 ? FAM : P.family;
+    const int t0 = blockIdx.y * BD_WIN;
+    const int m = min(P.m_non - t0, BD_WIN);     // terms of this window: t0 .. t0 + m - 1
     double* s_scale = s_dyn;
-    int* s_meta = reinterpret_cast<int*>(s_dyn + m);
+    int* s_meta = reinterpret_cast<int*>(s_dyn + BD_WIN);
     const int stride = 2 * (P.dense_maxord + 1);
     for (int j = threadIdx.x; j < m; j += T_BAS) { s_meta[j] = 0; s_scale[j] = 1.0; }   // default: constant term
     __syncthreads();
     for (int e = threadIdx.x; e < P.ndense * stride; e += T_BAS) {
-        const int j = P.ib[P.o_dense_idx + e];
-        if (j >= 0) {
+        const int j = P.ib[P.o_dense_idx + e] - t0;
+        if (j >= 0 && j < m) {
             const int g = e / stride, slot = e - g * stride;
             s_meta[j] = (1 << 31) | ((slot & 1) << 30) | ((slot >> 1) << 20) | P.ib[P.o_dense_var + 4 * g];
             s_scale[j] = P.db[P.o_d_dense_scale + e];
@@ -152,9 +160,13 @@ __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, co
     const int64_t base = (int64_t)blockIdx.x * T_BAS;
     const int64_t i = base + threadIdx.x;
     const int64_t ic = i < N ? i : N - 1;
+    const int nrow = (int)min((int64_t)T_BAS, N - base);
     int last_col = -1, cur = 0;                  // cached column; ladder state: pc = P_cur(x), pm = P_{cur-1}(x)
     double x = 0.0, ga = 0.0, pc = 1.0, pm = 0.0;
     bool have_ga = false;
+    // store mapping of a full window: thread -> (sample s0 + 8 it, term tt), 16 consecutive terms = 128 contiguous bytes
+    const int tt = threadIdx.x & (TJ_BAS - 1), s0 = threadIdx.x / TJ_BAS;
+    double* const out0 = Psi + (base + s0) * ldp + coff + t0 + tt;
     for (int j0 = 0; j0 < m; j0 += TJ_BAS) {
         const int w = min(TJ_BAS, m - j0);
         for (int t = 0; t < w; ++t) {
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, co
                 if (o < cur) { cur = 0; pc = 1.0; pm = 0.0; }   // orders usually ascend within a variable
                 for (; cur < o; ++cur) {         // three-term recurrence of the family up to order o
                     double A, B, C;
-                    rec_coef(P.family, cur, A, B, C);
+                    rec_coef(family, cur, A, B, C);
                     const double pn = fma(fma(A, x, B), pc, -C * pm);
                     pm = pc; pc = pn;
                 }
@@ -182,19 +194,30 @@ __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, co
             tile[t][threadIdx.x] = v;
         }
         __syncthreads();
-        if (w == TJ_BAS) {                       // full window: 16 consecutive terms of one sample = 128 contiguous bytes
-            for (int e = threadIdx.x; e < TJ_BAS * T_BAS; e += T_BAS) {
-                const int s = e >> 4, t = e & 15;
-                if (base + s < N) Psi[(base + s) * ldp + coff + j0 + t] = tile[t][s];
+        if (w == TJ_BAS) {
+            double* o = out0 + j0;
+#pragma unroll
+            for (int it = 0; it < T_BAS / (T_BAS / TJ_BAS); ++it) {
+                const int s = s0 + it * (T_BAS / TJ_BAS);
+                if (s < nrow) *o = tile[tt][s];
+                o += (T_BAS / TJ_BAS) * ldp;
             }
         } else {
             for (int e = threadIdx.x; e < w * T_BAS; e += T_BAS) {
                 const int s = e / w, t = e - s * w;
-                if (base + s < N) Psi[(base + s) * ldp + coff + j0 + t] = tile[t][s];
+                if (s < nrow) Psi[(base + s) * ldp + coff + t0 + j0 + t] = tile[t][s];
             }
         }
         __syncthreads();
     }
+}
+
+static void launch_basis_dense(const PlanView& P, const double* Xt, int64_t ld, int64_t N, double* Psi, int64_t ldp,
+                               cudaStream_t st) {
+    const dim3 grid((unsigned)((N + T_BAS - 1) / T_BAS), (unsigned)((P.m_non + BD_WIN - 1) / BD_WIN));
+    const size_t smem = BD_WIN * 12;
+    if (P.family == FAM_HERMITE_E) basis_dense_kernel<FAM_HERMITE_E><<<grid, T_BAS, smem, st>>>(P, Xt, ld, N, Psi, ldp, 0);
+    else basis_dense_kernel<-1><<<grid, T_BAS, smem, st>>>(P, Xt, ld, N, Psi, ldp, 0);
 }
 
 // 8 independent DFMA chains per thread
@@ -250,8 +273,8 @@ cudaError_t ttm_launch_basis(const PlanView& P, int which, const double* Xt, int
     else if (which == 1) { o_ptr = P.o_mon_ptr; o_fac = P.o_mon_fac; m = P.m_mon; }
     else { o_ptr = P.o_dmon_ptr; o_fac = P.o_dmon_fac; m = P.m_dmon; }
     if (m == 0 || N == 0) return cudaSuccess;
-    if (which == 0 && P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && m * 12 <= 30 * 1024)
-        basis_dense_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, m * 12, st>>>(P, Xt, ld, N, Psi, m, 0);
+    if (which == 0 && P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD)
+        launch_basis_dense(P, Xt, ld, N, Psi, m, st);
     else
         basis_kernel<<<(unsigned)((N + T_BAS - 1) / T_BAS), T_BAS, 0, st>>>(P, o_ptr, o_fac, m, Xt, ld, N, Psi, m, 0);
     return cudaGetLastError();
@@ -263,8 +286,8 @@ cudaError_t ttm_launch_basis_concat(const PlanView& P, const double* Xt, int64_t
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + T_BAS - 1) / T_BAS);
     if (P.m_non > 0) {
-        if (P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD && P.m_non * 12 <= 30 * 1024)
-            basis_dense_kernel<<<grid, T_BAS, P.m_non * 12, st>>>(P, Xt, ld, n, Psi, ldp, 0);
+        if (P.nvars == 0 && P.nmulti == 0 && P.dense_maxord <= BD_MAXORD)
+            launch_basis_dense(P, Xt, ld, n, Psi, ldp, st);
         else
             basis_kernel<<<grid, T_BAS, 0, st>>>(P, P.o_non_ptr, P.o_non_fac, P.m_non, Xt, ld, n, Psi, ldp, 0);
     }

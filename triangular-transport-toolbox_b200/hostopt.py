@@ -166,21 +166,25 @@ def _lb_advance(s, factr, pgtol, maxls, maxiter, maxfun):
             return False
 
 
-def lbfgsb_lockstep(x0s, bounds, launch, collect, ftol=2.2204460492503131e-09, gtol=1e-5, maxls=20, maxiter=15000,
-                    maxfun=15000):
+def lbfgsb_lockstep(x0s, bounds, launch=None, collect=None, ftol=2.2204460492503131e-09, gtol=1e-5, maxls=20,
+                    maxiter=15000, maxfun=15000, batch=None):
     """Minimise len(x0s) independent bound-constrained problems with scipy's L-BFGS-B core, in lockstep.
     bounds[i] = (lb, ub) arrays (+-inf for none); launch(i, x) starts the evaluation of problem i at x (x is only
-    valid during the call), collect(i) -> (f, grad) finishes it.  Returns one Result per problem."""
+    valid during the call), collect(i) -> (f, grad) finishes it; or batch(idx, xs) -> [(f, grad), ...] evaluates
+    the listed problems in one call.  Returns one Result per problem."""
     factr = ftol / np.finfo(float).eps
     states = [_LbState(np.asarray(x0, dtype=np.float64).ravel(), np.asarray(b[0], dtype=np.float64),
                        np.asarray(b[1], dtype=np.float64)) for x0, b in zip(x0s, bounds)]
     active = list(range(len(states)))
     while active:
         want = [i for i in active if _lb_advance(states[i], factr, gtol, maxls, maxiter, maxfun)]
-        for i in want:
-            launch(i, states[i].x)
-        for i in want:
-            f, g = collect(i)
+        if batch is not None:
+            got = batch(want, [states[i].x for i in want]) if want else []
+        else:
+            for i in want:
+                launch(i, states[i].x)
+            got = [collect(i) for i in want]
+        for i, (f, g) in zip(want, got):
             s = states[i]
             s.f = float(f)
             s.g = np.asarray(g, dtype=np.float64)

@@ -926,7 +926,30 @@ class transport_map():
             Ng = self._N_global
             return b @ Ax / 2 - out[0] / Ng + b @ bvec, Ax - out[1:] / Ng + bvec
 
-        res = hostopt.lbfgsb_lockstep(x0s, bnds, launch, collect)
+        if self._sharded:
+            res = hostopt.lbfgsb_lockstep(x0s, bnds, launch, collect)
+        else:
+            # one C call per round: queue every K-sepobj launch, collect, assemble (f, g) of the reduced problem
+            ct = B.ctypes
+            vp = ct.c_void_p
+            Ab = [np.ascontiguousarray(setups[k][0]) for k in comps]
+            cb = [np.ascontiguousarray(setups[k][2]) for k in comps]
+            bb = [np.empty(len(x)) for x in x0s]
+            fg = [np.empty(1 + len(x)) for x in x0s]
+            addr = lambda arrs: [a.ctypes.data for a in arrs]
+            pA, pc, pb, pfg = addr(Ab), addr(cb), addr(bb), addr(fg)
+            pl = [self._plans[k].value if hasattr(self._plans[k], 'value') else self._plans[k] for k in comps]
+            Ng = float(self._N_global)
+
+            def batch(idx, xs):
+                n = len(idx)
+                for i, x in zip(idx, xs):
+                    bb[i][:] = x
+                arr = lambda src: (vp * n)(*[src[i] for i in idx])
+                B.check(lib.ttm_sep_reduced_batch(n, arr(pl), Xp, ld, N, Ng, arr(pb), arr(pA), arr(pc), arr(pfg), st))
+                return [(fg[i][0], fg[i][1:].copy()) for i in idx]
+
+            res = hostopt.lbfgsb_lockstep(x0s, bnds, batch=batch)
         results = {}
         for k, opt in zip(comps, res):
             self._last_opt = opt
