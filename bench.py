@@ -76,8 +76,10 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            # -i: this rank's GPU only (every rank polling every GPU is N^2 driver queries per period)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 p = [t.strip() for t in line.split(',')]
                 if len(p) >= 8 and p[0] == str(self.gpu_index) and self.active:
