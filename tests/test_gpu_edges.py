@@ -189,7 +189,7 @@ def test_pipelined_inverse_is_bit_identical_to_one_shot(conditioning, monkeypatc
     monkeypatch.setenv('TTM_INV_PIPELINE_MIN', '1000000000')
     one_shot = tm.inverse_map(Z, X_star=Xs)
     monkeypatch.setenv('TTM_INV_PIPELINE_MIN', '1000')
-    monkeypatch.setenv('TTM_INV_CHUNK', '600')          # 5 chunks of 501 through 3 slots, the last one ragged (499)
+    monkeypatch.setenv('TTM_INV_CHUNK', '600')          # 5 chunks of 501 through 4 slots, the last one (499) cut into 248 + 124 + 127
     piped = tm.inverse_map(Z, X_star=Xs)
     assert piped.shape == one_shot.shape
     assert np.array_equal(piped, one_shot)

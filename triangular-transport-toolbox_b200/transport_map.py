@@ -1094,26 +1094,17 @@ class transport_map():
             tabs[r] = self._upload(np.concatenate((vals[r][ind], pts[ind])))
         return tabs
 
-    def _inverse_fused_setup(self, comps, resolution=1001):
-        """Operands of K-inv-fused (ttm_inverse_fused: the component loop of tm.py:3684-3698 in one launch), or None if
-        some component is outside its class (nonmonotone terms other than constants and per-variable Hermite-function
-        groups of order <= 3, components not on consecutive columns)."""
-        if not comps or os.environ.get('TTM_INV_FUSED', '1') == '0':
-            return None
+    def _inverse_fused_static(self, ks, mode):
+        """The part of the K-inv-fused / K-inv-rect operands that depends on the term lists only (class check, slot set,
+        packed destination of every coefficient), cached until the plans are recompiled: a conditional-sampling loop
+        with changing coefficients (EnTF cycles, adaptation) pays one gather/scatter per call instead of a walk over
+        every dense group of every component."""
         from .plan import FAM_HERMITE_E
-        ks = [k for _, k in comps]
-        # operands depend on the coefficients and the special-term placement only: repeated calls (sampling in batches,
-        # the chunks of one call) reuse them
-        import hashlib
-        h = hashlib.blake2b(digest_size=16)
-        for k in ks:
-            h.update(np.ascontiguousarray(self.coeffs_nonmon[k], dtype=np.float64).tobytes())
-            h.update(np.ascontiguousarray(self.coeffs_mon[k], dtype=np.float64).tobytes())
-        mode = os.environ.get('TTM_INV_SPLIT', 'auto')
-        key = (tuple(ks), resolution, self._ensemble_version, h.digest(), mode)
-        hit = getattr(self, '_inv_fused_cache', None)
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        cache = self.__dict__.setdefault('_inv_pack_cache', {})
+        skey = (tuple(ks), mode)
+        if skey in cache:
+            return cache[skey]
+        cache[skey] = None
         plans = [self._host_plans[k] for k in ks]
         c0 = plans[0].c
         if self._family != FAM_HERMITE_E or any(p.c != c0 + j for j, p in enumerate(plans)):
@@ -1130,44 +1121,74 @@ class transport_map():
         ns, CB, ncomp = len(slots), 16, len(ks)
         size = B.c_int64()
         B.check(self._lib.ttm_inverse_fused_apack_size(ncomp, c0, ns, B.ctypes.byref(size)))
-        A = np.zeros(size.value)
-        a0 = np.zeros(ncomp)
+        a_size = size.value
         # wide conditioning block: its share of the offsets is one GEMM (K-inv-rect) ahead of the sequential walk
         split = c0 > 0 and mode != '0' and (mode == '1' or (c0 >= 32 and ncomp >= 32))
         c0p = (c0 + 7) // 8 * 8
+        r_size = 0
         if split:
             B.check(self._lib.ttm_inverse_rect_rpack_size(ncomp, c0, ns, B.ctypes.byref(size)))
-            R = np.zeros(size.value)
-        cache = self.__dict__.setdefault('_inv_pack_cache', {})
+            r_size = size.value
+        dst, src, sc, rdst, const_src, const_ptr = [], [], [], [], [], [0]
+        off = 0                                                            # offset of component j in the concatenated coefficients
         for j, (k, p) in enumerate(zip(ks, plans)):
-            cn = np.asarray(self.coeffs_nonmon[k], dtype=np.float64)
-            a0[j] = sum(cn[q] for q in p.const_idx)
-            key = (k, c0, j, ns)
-            if key not in cache:                                           # static part of the packing, per component
-                b, jj = divmod(j, CB)
-                row0 = b * (c0 + CB) + CB * b * (b - 1) // 2
-                dst, src, sc, rdst = [], [], [], []
-                for v, idx_row, sc_row in p.dense_groups:
-                    if v >= c0 + j:
-                        cache[key] = None                                  # not a triangular dependency
-                        break
-                    for q, sl in enumerate(slots):
-                        if sl < len(idx_row) and idx_row[sl] >= 0:
-                            dst.append(((row0 + v) * CB + jj) * ns + q)
-                            src.append(int(idx_row[sl]))
-                            sc.append(float(sc_row[sl]))
-                            # K-inv-rect operand [j // 128][v][slot][j % 128]; -1: a column the walk itself solves
-                            rdst.append((((j // 128) * c0p + v) * ns + q) * 128 + j % 128 if v < c0 else -1)
-                else:
-                    cache[key] = (np.asarray(dst, dtype=np.int64), np.asarray(src, dtype=np.int64), np.asarray(sc),
-                                  np.asarray(rdst, dtype=np.int64))
-            if cache[key] is None:
-                return None
-            dst, src, sc, rdst = cache[key]
-            A[dst] = cn[src] * sc
-            if split:
-                keep = rdst >= 0
-                R[rdst[keep]] = (cn[src] * sc)[keep]
+            b, jj = divmod(j, CB)
+            row0 = b * (c0 + CB) + CB * b * (b - 1) // 2
+            for v, idx_row, sc_row in p.dense_groups:
+                if v >= c0 + j:
+                    return None                                            # not a triangular dependency
+                for q, sl in enumerate(slots):
+                    if sl < len(idx_row) and idx_row[sl] >= 0:
+                        dst.append(((row0 + v) * CB + jj) * ns + q)
+                        src.append(off + int(idx_row[sl]))
+                        sc.append(float(sc_row[sl]))
+                        # K-inv-rect operand [j // 128][v][slot][j % 128]; -1: a column the walk itself solves
+                        rdst.append((((j // 128) * c0p + v) * ns + q) * 128 + j % 128 if v < c0 else -1)
+            const_src += [off + int(q) for q in p.const_idx]
+            const_ptr.append(len(const_src))
+            off += p.m_non
+        rdst = np.asarray(rdst, dtype=np.int64)
+        rkeep = rdst >= 0
+        cache[skey] = {'ncomp': ncomp, 'c0': c0, 'ns': ns, 'split': split, 'a_size': a_size, 'r_size': r_size,
+                       'dst': np.asarray(dst, dtype=np.int64), 'src': np.asarray(src, dtype=np.int64),
+                       'sc': np.asarray(sc), 'rdst': rdst[rkeep], 'rkeep': rkeep,
+                       'const_src': np.asarray(const_src, dtype=np.int64),
+                       'const_ptr': np.asarray(const_ptr, dtype=np.int64)}
+        return cache[skey]
+
+    def _inverse_fused_setup(self, comps, resolution=1001):
+        """Operands of K-inv-fused (ttm_inverse_fused: the component loop of tm.py:3684-3698 in one launch), or None if
+        some component is outside its class (nonmonotone terms other than constants and per-variable Hermite-function
+        groups of order <= 3, components not on consecutive columns)."""
+        if not comps or os.environ.get('TTM_INV_FUSED', '1') == '0':
+            return None
+        ks = [k for _, k in comps]
+        # operands depend on the coefficients and the special-term placement only: repeated calls (sampling in batches,
+        # the chunks of one call) reuse them
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        for k in ks:
+            h.update(np.ascontiguousarray(self.coeffs_nonmon[k], dtype=np.float64).tobytes())
+            h.update(np.ascontiguousarray(self.coeffs_mon[k], dtype=np.float64).tobytes())
+        mode = os.environ.get('TTM_INV_SPLIT', 'auto')
+        key = (tuple(ks), resolution, self._ensemble_version, h.digest(), mode)
+        hit = getattr(self, '_inv_fused_cache', None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        st = self._inverse_fused_static(ks, mode)
+        if st is None:
+            return None
+        ncomp, c0, ns, split = st['ncomp'], st['c0'], st['ns'], st['split']
+        # dynamic part: coefficient * scale scattered into the packed operands, all components at once
+        cat = np.concatenate([np.asarray(self.coeffs_nonmon[k], dtype=np.float64) for k in ks])
+        val = cat[st['src']] * st['sc']
+        A = np.zeros(st['a_size'])
+        A[st['dst']] = val
+        cp, cs = st['const_ptr'], st['const_src']
+        a0 = np.array([sum(cat[q] for q in cs[cp[j]:cp[j + 1]]) for j in range(ncomp)], dtype=np.float64)
+        if split:
+            R = np.zeros(st['r_size'])
+            R[st['rdst']] = val[st['rkeep']]
         fused = {'ncomp': ncomp, 'c0': c0, 'ns': ns, 'A': self._upload(A), 'a0': self._upload(a0),
                  'tabs': self._monotone_tables(comps, resolution=resolution), 'ntab': resolution,
                  'R': self._upload(R) if split else None}
@@ -1213,9 +1234,12 @@ class transport_map():
 
     def _inverse_map_pipelined(self, Z, X_star, E, ncol, comps, resolution=1001):
         """Table-mode inverse_map for large sample counts.  Samples are independent (tm.py:3684-3698 loops over the
-        components, never across samples), so the call is cut into chunks of samples that flow through three
-        slots: host threads stage chunk c+1 into pinned memory while chunk c is copied, transposed, solved (one
-        K-inv-table launch per component) and chunk c-1 is copied back.  Bit-identical to the one-shot path."""
+        components, never across samples), so the call is cut into chunks of samples that flow through four
+        slots: host threads stage chunk c+1 into pinned memory (page-locked inputs are copied from directly) while
+        chunk c is copied, transposed and solved and chunk c-1 is copied back.  The call is bound by the host->device
+        copies (torch.profiler timeline: 16 copies of 168 MB at 52-58 GB/s back to back); four slots keep a copy from
+        waiting for the slot's previous result to leave, and the last chunks are short so that little of the final
+        solve + copy-back is exposed.  Bit-identical to the one-shot path."""
         from concurrent.futures import ThreadPoolExecutor
         torch, lib, dev = self._torch, self._lib, self._device
         N, nz, skip = Z.shape[0], Z.shape[1], self.skip_dimensions
@@ -1234,14 +1258,29 @@ class transport_map():
         torch.cuda.current_stream(dev).synchronize()
         nchunk = max(2, -(-N // int(os.environ.get('TTM_INV_CHUNK', 163840))))
         cap = -(-N // nchunk)
-        nslot = min(3, nchunk)
+        # chunk boundaries: equal chunks, the last one cut into 1/2, 1/4, 1/4
+        bounds = [min(N, c * cap) for c in range(nchunk + 1)]
+        if nchunk >= 4 and bounds[-1] - bounds[-2] >= 64:
+            lo, hi = bounds[-2], bounds[-1]
+            q = (hi - lo) // 4
+            bounds = bounds[:-1] + [lo + 2 * q, lo + 3 * q, hi]
+        bounds = [b for i, b in enumerate(bounds) if i == 0 or b > bounds[i - 1]]
+        nslot = min(int(os.environ.get('TTM_INV_SLOTS', 4)), len(bounds) - 1)
         f64 = torch.float64
+
+        def pinned(a):                                       # caller's array already page-locked: DMA straight from it
+            if a is None or not a.flags['C_CONTIGUOUS'] or a.dtype != np.float64:
+                return False
+            flag = B.c_int(0)
+            B.check(lib.ttm_host_is_pinned(B.c_void_p(a.ctypes.data), B.ctypes.byref(flag)))
+            return bool(flag.value)
+        z_pinned, x_pinned = pinned(Z), pinned(X_star)
         slots = []
         for _ in range(nslot):
             slots.append({
                 'stream': torch.cuda.Stream(device=dev), 'event': None,
-                'hz': torch.empty((cap, nz), dtype=f64, pin_memory=True),
-                'hx': torch.empty((cap, E), dtype=f64, pin_memory=True) if E > 0 else None,
+                'hz': torch.empty((cap, nz), dtype=f64, pin_memory=True) if not z_pinned else None,
+                'hx': torch.empty((cap, E), dtype=f64, pin_memory=True) if (E > 0 and not x_pinned) else None,
                 'dz': torch.empty((cap, nz), dtype=f64, device=dev),
                 'dx': torch.empty((cap, E), dtype=f64, device=dev) if E > 0 else None,
                 'Xw': torch.empty((ncol, cap), dtype=f64, device=dev),
@@ -1259,20 +1298,10 @@ class transport_map():
             return [pool.submit(np.copyto, dst[edges[t]:edges[t + 1]], src[edges[t]:edges[t + 1]])
                     for t in range(nthr) if edges[t + 1] > edges[t]]
 
-        def pinned(a):                                       # caller's array already page-locked: DMA straight from it
-            if a is None or not a.flags['C_CONTIGUOUS'] or a.dtype != np.float64:
-                return False
-            flag = B.c_int(0)
-            B.check(lib.ttm_host_is_pinned(B.c_void_p(a.ctypes.data), B.ctypes.byref(flag)))
-            return bool(flag.value)
-        z_pinned, x_pinned = pinned(Z), pinned(X_star)
-
         with ThreadPoolExecutor(nthr) as pool:
-            for c in range(nchunk):
-                c0, c1 = c * cap, min(N, (c + 1) * cap)
+            for c in range(len(bounds) - 1):
+                c0, c1 = bounds[c], bounds[c + 1]
                 n = c1 - c0
-                if n <= 0:
-                    break
                 sl = slots[c % nslot]
                 if sl['event'] is not None:
                     sl['event'].synchronize()                # the slot's previous chunk is back on the host
