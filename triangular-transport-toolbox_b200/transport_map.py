@@ -404,6 +404,7 @@ class transport_map():
     # ================================================================== plans
     def _compile_plans(self):
         self._inv_pack_cache = {}
+        self._donor_cache = None
         self._host_plans = []
         for k in range(self.D):
             self._host_plans.append(ComponentPlan(
@@ -447,6 +448,7 @@ class transport_map():
             self._plans[k] = self._create_plan(p)
             self._plan_info[k] = self._query_plan(self._plans[k])
             self._inv_pack_cache = {}
+            self._donor_cache = None
         else:
             raise Exception("'k' for function_constructor_alternative must be either None or an integer.")
         if self.monotonicity.lower() == 'separable monotonicity':
@@ -672,16 +674,25 @@ class transport_map():
         Gram matrix contains G_k as the leading block, so one K-gram launch serves every component of a map whose
         components share their basis (C4: nonmonotone[k] is a prefix of nonmonotone[D-1]).  Special terms are
         placed per component (tm.py:2241-2330), so lists containing them are not shared."""
-        spec = self.nonmonotone[k]
-        if any(type(e) == str for e in spec):
-            return k
-        best = k
-        for kk in range(self.D):
-            other = self.nonmonotone[kk]
-            if len(other) > len(self.nonmonotone[best]) and other[:len(spec)] == spec and \
-                    not any(type(e) == str for e in other):
-                best = kk
-        return best
+        dm = getattr(self, '_donor_cache', None)
+        if dm is None:
+            # one pass over the components, longest list first: a list's donor is always a root (a list that is no
+            # proper prefix of a longer one), so only roots are compared (list equality runs at C speed)
+            has_str = [any(type(e) == str for e in self.nonmonotone[kk]) for kk in range(self.D)]
+            roots, dm = [], {}
+            for kk in sorted(range(self.D), key=lambda q: (-len(self.nonmonotone[q]), q)):
+                spec = self.nonmonotone[kk]
+                dm[kk] = kk
+                if has_str[kk]:
+                    continue
+                for r in roots:
+                    if self.nonmonotone[r][:len(spec)] == spec:
+                        dm[kk] = r
+                        break
+                else:
+                    roots.append(kk)
+            self._donor_cache = dm
+        return dm[k]
 
     def _gram_nonmon(self, k):
         """G = Psi_non^T Psi_non / N of component k (K-gram, once per ensemble -- the counterpart of the reference's
@@ -1291,7 +1302,9 @@ class transport_map():
         out_host = torch.empty((N, nout), dtype=f64, pin_memory=True)
         trunc = 1 if self.root_search_truncation else 0
         ptr = lambda t: B.c_void_p(t.data_ptr()) if t is not None else None
-        nthr = 4
+        # host threads of the pageable -> pinned staging copies (memcpy-bound: ~8 GB/s per thread against 55 GB/s of PCIe)
+        from .parallel import world as _world
+        nthr = int(os.environ.get('TTM_INV_STAGE_THREADS', 0)) or max(2, min(8, (os.cpu_count() or 8) // max(1, _world()[1])))
 
         def stage(dst, src, n):                              # pageable -> pinned, split over host threads
             edges = [n * t // nthr for t in range(nthr + 1)]
