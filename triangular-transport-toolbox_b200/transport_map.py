@@ -998,6 +998,9 @@ class transport_map():
 
             def run(k):
                 if not hasattr(tls, 'stream'):
+                    # a new host thread starts on device 0: bind it to this map's GPU first, or the stream context
+                    # below would query (and so create a context on) device 0 from every rank
+                    torch.cuda.set_device(self._device)
                     tls.stream = torch.cuda.Stream(device=self._device)
                     tls.stream.wait_stream(main_stream)      # the ensemble was produced on the caller's stream
                 with torch.cuda.stream(tls.stream):
