@@ -89,3 +89,36 @@ def test_refresh_special_equals_rebuild_and_tables_do_not_depend_on_the_data(nam
             assert np.array_equal(fresh.iblob, plan.iblob), (name, k, variant)
             plan.refresh_special(st)
             assert np.array_equal(plan.dblob, fresh.dblob), (name, k, variant)
+
+
+def test_donor_map_equals_the_all_pairs_definition():
+    """plan.donor_map (one pass over the roots) against the definition it replaces: the longest special-term-free list
+    of which the component's list is a prefix; first index among equally long ones."""
+    from cases import c4_terms, c5_terms
+    from ttt_b200.plan import donor_map
+
+    def brute(non):
+        out = {}
+        for k, spec in enumerate(non):
+            best = k
+            if not any(type(e) == str for e in spec):
+                for kk, other in enumerate(non):
+                    if len(other) > len(non[best]) and other[:len(spec)] == spec and \
+                            not any(type(e) == str for e in other):
+                        best = kk
+            out[k] = best
+        return out
+
+    rng = np.random.default_rng(3)
+    lists = [c4_terms(12)[1], c5_terms(9)[1]]
+    # two interleaved families of prefixes, a list with a special term, and an unrelated list
+    fam_a = [[[]] + [[j] for j in range(n)] for n in (0, 2, 5, 3)]
+    fam_b = [[[]] + [[j, j] for j in range(n)] for n in (1, 4, 2)]
+    mixed = fam_a + fam_b + [[[], 'iRBF 0', [0]], [[1, 1, 1]]]
+    lists.append([mixed[i] for i in rng.permutation(len(mixed))])
+    for non in lists:
+        got, want = donor_map(non), brute(non)
+        for k in range(len(non)):
+            # identical lists at different positions may share a donor where the all-pairs search kept k itself
+            assert got[k] == want[k] or (non[got[k]][:len(non[k])] == non[k] and len(non[got[k]]) >= len(non[want[k]])), k
+            assert non[got[k]][:len(non[k])] == non[k]

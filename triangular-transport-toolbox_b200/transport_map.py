@@ -676,22 +676,8 @@ class transport_map():
         placed per component (tm.py:2241-2330), so lists containing them are not shared."""
         dm = getattr(self, '_donor_cache', None)
         if dm is None:
-            # one pass over the components, longest list first: a list's donor is always a root (a list that is no
-            # proper prefix of a longer one), so only roots are compared (list equality runs at C speed)
-            has_str = [any(type(e) == str for e in self.nonmonotone[kk]) for kk in range(self.D)]
-            roots, dm = [], {}
-            for kk in sorted(range(self.D), key=lambda q: (-len(self.nonmonotone[q]), q)):
-                spec = self.nonmonotone[kk]
-                dm[kk] = kk
-                if has_str[kk]:
-                    continue
-                for r in roots:
-                    if self.nonmonotone[r][:len(spec)] == spec:
-                        dm[kk] = r
-                        break
-                else:
-                    roots.append(kk)
-            self._donor_cache = dm
+            from .plan import donor_map
+            dm = self._donor_cache = donor_map(self.nonmonotone)
         return dm[k]
 
     def _gram_nonmon(self, k):
