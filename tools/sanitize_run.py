@@ -1,5 +1,5 @@
 """Small exercise of every round-2 kernel for compute-sanitizer (memcheck / racecheck):
-tile K-objgrad (Gram and two-sweep forms, partial tiles), K-S, K-gram + tail, dense K-basis, K-inv-fused,
+tile K-objgrad (Gram and two-sweep forms, partial tiles), K-S, K-gram + tail, dense K-basis, K-inv-fused, K-inv-rect,
 K-map-fused (map / pullback / pushforward), K-sepobj with the mapped result mirror."""
 import os
 import sys
@@ -38,6 +38,25 @@ for k in range(D):
     ts.coeffs_mon[k], ts.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
 X = ts.inverse_map(rng.standard_normal((n, D - E)), X_star=synthetic_samples(n, D, seed=4)[:, :E].copy())
 assert np.all(np.isfinite(X))
+# K-inv-rect (DMMA GEMM over the conditioning block) + the walk with staged tables: conditioning width that is no
+# multiple of the 8-variable chunk, sample count that is no multiple of the 64-sample tile; 3- and 6-slot operands
+os.environ['TTM_INV_SPLIT'] = '1'
+for mixed in (False, True):
+    D, E, n = 21, 9, 333
+    mon, non = c5_terms(D)
+    if mixed:
+        non = [[[]] + [t for j in range(k) for t in ([j], [j, 'HF'], [j, j], [j, j, 'HF'], [j, j, j], [j, j, j, 'HF'])]
+               for k in range(D)]
+    tq = transport_map(X=synthetic_samples(400, D, seed=6), monotone=mon, nonmonotone=non,
+                       monotonicity='separable monotonicity', verbose=False)
+    cm, cn = headline_sep_coeffs(mon, non)
+    for k in range(D):
+        tq.coeffs_mon[k], tq.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
+    fz = tq._inverse_fused_setup([(i, k) for i, k in enumerate(range(E, D))])
+    assert fz is not None and fz['R'] is not None
+    X = tq.inverse_map(rng.standard_normal((n, D - E)), X_star=synthetic_samples(n, D, seed=7)[:, :E].copy())
+    assert np.all(np.isfinite(X))
+del os.environ['TTM_INV_SPLIT']
 mon, non = ex05_terms()
 t5 = transport_map(X=synthetic_samples(400, 2, seed=5), monotone=mon, nonmonotone=non,
                    monotonicity='separable monotonicity', verbose=False)
