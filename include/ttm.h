@@ -160,6 +160,18 @@ int ttm_gram(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, double* G,
 int ttm_gram_tail(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, int first_col, double* G, double* scratch,
                   int64_t scratch_doubles, void* stream);
 
+/* ---- forward map of a wide separable map as a GEMM --------------------------------------------
+ * replaces: the nonmonotone sums of `s` (tm.py:2550-2558) for ALL components of `map` (:2391-2437) at once.  With
+ * every column known, sum_{v<c} sum_q f_q(x_iv) a[v][q][c] is a (block-triangular) FP64 GEMM: ttm_map_rect runs
+ * K-inv-rect over `rows` variables with component j using the rows v < first + j (Rpack as for
+ * ttm_inverse_fused_split, zero elsewhere; tiles skip the rows no component of theirs uses), base = [ncomp][ldb].
+ * ttm_sep_eval_base then adds the constant a0 and the monotone terms of one component: S = base + a0 + mon(x_c).
+ * The per-component path (ttm_sep_eval) re-reads every predecessor column for every component: 8 n D^2 / 2 bytes. */
+int ttm_map_rect(ttm_ctx* ctx, const double* Xt, int64_t ld, int64_t N, int ncomp, int rows, int ns, int first,
+                 const double* Rpack, double* base, int64_t ldb, void* stream);
+int ttm_sep_eval_base(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, const double* base, double a0,
+                      double* S_out, void* stream);
+
 /* ---- K-sepobj ---------------------------------------------------------------------------------
  * replaces: the sample-dependent part of fun_mon_objective, tm.py:2990-3006.
  * host_out[0] = sum_i log dS_i, host_out[1+j] = sum_i dPsi_ij / dS_i with

@@ -264,6 +264,34 @@ def test_split_inverse_matches_the_oracle(D, E, n, mixed, monkeypatch):
     assert rel_err(tm.inverse_map(Z.copy(), xs()), got) <= 1e-12
 
 
+@pytest.mark.parametrize('D,n,mixed', [(40, 4100, False), (34, 4097, True), (150, 4160, False)])
+def test_gemm_forward_map_matches_the_oracle(D, n, mixed, monkeypatch):
+    """map() of a wide separable map: nonmonotone sums of all components as one block-triangular DMMA GEMM
+    (ttm_map_rect) + monotone terms per component (ttm_sep_eval_base), against the oracle and the per-component
+    kernels; sample counts off the 64-sample tile, 3- and 6-slot operands, two component tiles (D = 150)."""
+    from cases import c5_terms, headline_sep_coeffs
+    mon, non = c5_terms(D)
+    if mixed:
+        non = [[[]] + [t for j in range(k) for t in ([j], [j, 'HF'], [j, j], [j, j, 'HF'], [j, j, j], [j, j, j, 'HF'])]
+               for k in range(D)]
+    X = synthetic_samples(400, D, seed=25)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+    tm = make_cuda(X.copy(), **kw)
+    om = make_oracle(X.copy(), **kw)
+    cm, cn = headline_sep_coeffs(mon, non)
+    for k in range(D):
+        tm.coeffs_mon[k], tm.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
+        om.coeffs_mon[k], om.coeffs_nonmon[k] = cm[k].copy(), cn[k].copy()
+    Xe = synthetic_samples(n, D, seed=26)
+    assert tm._map_gemm_static() is not None
+    got = tm.map(Xe.copy())
+    assert rel_err(got, om.map(Xe.copy())) <= 1e-10
+    monkeypatch.setenv('TTM_MAP_GEMM', '0')
+    tm._inv_pack_cache.pop('map_gemm', None)
+    assert tm._map_gemm_static() is None
+    assert rel_err(tm.map(Xe.copy()), got) <= 1e-12
+
+
 @pytest.mark.parametrize('name', ['sep_ex05', 'sep_ex06_cycle', 'sep_c5_d6'])
 def test_per_component_paths_match_the_fused_ones(name, monkeypatch):
     """map / inverse_map / densities through the per-component kernels (TTM_MAP_FUSED=0, TTM_INV_FUSED=0: the paths

@@ -74,6 +74,9 @@ def lib():
             'ttm_inverse_fused': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_int, c_int, c_void_p],
             'ttm_inverse_rect_rpack_size': [c_int, c_int, c_int, ctypes.POINTER(c_int64)],
+            'ttm_map_rect': [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                             c_int64, c_void_p],
+            'ttm_sep_eval_base': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, ctypes.c_double, c_void_p, c_void_p],
             'ttm_inverse_fused_split': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p],
             'ttm_inverse_bisect': [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,

@@ -426,6 +426,28 @@ int ttm_sep_eval(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, double* S
     return TTM_OK;
 }
 
+int ttm_map_rect(ttm_ctx* c, const double* Xt, int64_t ld, int64_t N, int ncomp, int rows, int ns, int first,
+                 const double* Rpack, double* base, int64_t ldb, void* stream) {
+    if (!c || !Xt || !Rpack || !base || N <= 0 || ld < N || ldb < N || ncomp <= 0 || rows <= 0 || first < 0)
+        return fail(TTM_ERR_ARG, "ttm_map_rect: bad arguments");
+    if (ns != 3 && ns != 6) return fail(TTM_ERR_ARG, "ttm_map_rect: ns must be 3 or 6");
+    CK(cudaSetDevice(c->device));
+    InvRectArgs r;
+    r.Xw = Xt; r.ld = ld; r.N = N; r.ncomp = ncomp; r.c0 = rows; r.ns = ns; r.Rpack = Rpack; r.base = base; r.ldb = ldb;
+    r.tri = first;
+    CK(ttm_launch_inverse_rect(r, c->sm_count, (cudaStream_t)stream));
+    return TTM_OK;
+}
+
+int ttm_sep_eval_base(ttm_plan* p, const double* Xt, int64_t ld, int64_t N, const double* base, double a0, double* S_out,
+                      void* stream) {
+    if (!p || !Xt || !base || !S_out || N <= 0 || ld < N) return fail(TTM_ERR_ARG, "ttm_sep_eval_base: bad arguments");
+    CK(cudaSetDevice(p->ctx->device));
+    CK(ttm_launch_sep_eval(p->view, Xt, ld, N, p->d_coeffs, S_out, nullptr, 0, nullptr, p->ctx->sm_count,
+                           (cudaStream_t)stream, base, a0));
+    return TTM_OK;
+}
+
 int ttm_density_accumulate(ttm_ctx* c, double* acc, const double* S, const double* dS, double sigma, int mode,
                            int64_t N, void* stream) {
     if (!c || !acc || !dS || (mode == 0 && !S) || N <= 0) return fail(TTM_ERR_ARG, "ttm_density_accumulate: bad arguments");
@@ -651,6 +673,7 @@ int ttm_inverse_fused_split(ttm_ctx* c, double* Xw, int64_t ld, int64_t N, const
     CK(cudaSetDevice(c->device));
     InvRectArgs r;
     r.Xw = Xw; r.ld = ld; r.N = N; r.ncomp = ncomp; r.c0 = c0; r.ns = ns; r.Rpack = Rpack; r.base = base; r.ldb = ldb;
+    r.tri = -1;
     CK(ttm_launch_inverse_rect(r, c->sm_count, (cudaStream_t)stream));
     InvFusedArgs a;
     a.Xw = Xw; a.ld = ld; a.N = N; a.Zt = Zt; a.ldz = ldz; a.ncomp = ncomp; a.c0 = c0; a.ns = ns;

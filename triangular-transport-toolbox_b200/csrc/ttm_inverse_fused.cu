@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(TB, 2) inverse_rect_kernel(const InvRectArgs a
     const int64_t tiles = (a.N + TS - 1) / TS;
     const int nsb = (a.ncomp + TC - 1) / TC;
     const int c0p = (a.c0 + 7) / 8 * 8;                      // packed rows per component tile (zero padded)
-    const int nchunk = (a.c0 + VC - 1) / VC;
+    const int nchunk_all = (a.c0 + VC - 1) / VC;
     __syncthreads();
     for (int64_t w = blockIdx.x; w < tiles * nsb; w += gridDim.x) {
         const int64_t tile = w / nsb;
@@ -387,6 +387,8 @@ __global__ void __launch_bounds__(TB, 2) inverse_rect_kernel(const InvRectArgs a
         const int64_t i0 = tile * TS;
         const int64_t irow = min(i0 + fs, a.N - 1);
         const double* Ab = a.Rpack + (int64_t)sb * c0p * NS * TC;
+        const int nchunk = (a.tri < 0) ? nchunk_all
+                                       : (min(a.c0, a.tri + TC * (sb + 1)) + VC - 1) / VC;   // rows beyond are zero
         auto stage = [&](int ch, int buf) {
             const double* src = Ab + (int64_t)ch * KR * TC;
             double* dst = sA + buf * KR * AS;

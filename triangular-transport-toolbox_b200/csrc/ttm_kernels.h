@@ -64,7 +64,7 @@ cudaError_t ttm_launch_basis_concat(const PlanView& P, const double* Xt, int64_t
 // separable-monotonicity evaluation: S_k and d_k S_k per sample (reference: s :2550-2558, densities :2620-2641)
 cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* coeffs,
                                 double* S_out, const double* Xd, int64_t ldd, double* dS_out, int sm_count,
-                                cudaStream_t st);
+                                cudaStream_t st, const double* base = nullptr, double a0 = 0.0);
 
 cudaError_t ttm_launch_density_acc(double* acc, const double* S, const double* dS, double sigma, int mode, int64_t N,
                                    cudaStream_t st);
@@ -146,8 +146,10 @@ struct InvRectArgs {
     int64_t ld, N;
     int ncomp, c0, ns;
     const double* Rpack;   // [ceil(ncomp/128)][c0 rounded up to 8][ns][128], zero padded
-    double* base;          // [ncomp][ldb], 16-byte aligned, ldb even
+    double* base;          // [ncomp][ldb]
     int64_t ldb;
+    int tri;               // -1: every component uses all c0 rows; >= 0: component j uses the rows v < tri + j only (the
+                           // forward map: all columns known, Rpack is triangular) -- tile sb stops at tri + 128 (sb + 1)
 };
 cudaError_t ttm_launch_inverse_rect(const InvRectArgs& a, int sm_count, cudaStream_t st);
 size_t ttm_inverse_rect_rpack_doubles(int ncomp, int c0, int ns);

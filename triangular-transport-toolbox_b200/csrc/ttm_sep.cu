@@ -16,7 +16,10 @@ constexpr int T_SEP = 128;
 __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
                                                          int64_t N, const double* __restrict__ coeffs,
                                                          double* __restrict__ S_out, const double* __restrict__ Xd,
-                                                         int64_t ldd, double* __restrict__ dS_out) {
+                                                         int64_t ldd, double* __restrict__ dS_out,
+                                                         const double* __restrict__ base, double a0) {
+    // base != NULL: the nonmonotone part comes from K-inv-rect's GEMM (base_i + a0), only the monotone terms are
+    // evaluated here
     extern __shared__ double s_coef[];
     const int m = P.m_non + P.m_mon;
     for (int j = threadIdx.x; j < m; j += T_SEP) s_coef[j] = coeffs[j];
@@ -37,8 +40,13 @@ __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const
             S[r] = 0.0;
         }
         if (S_out) {
-            dense_value_smem_rt<R_OBJ>(P, DS, Xt, ld, row0 * T_SEP + threadIdx.x, T_SEP, ok, S);
-            nonmon_slow_rt<false>(P, Xt, ld, idx, acoef, S, nullptr, 0);
+            if (base) {
+#pragma unroll
+                for (int r = 0; r < R_OBJ; ++r) S[r] = __ldcs(base + idx[r]) + a0;
+            } else {
+                dense_value_smem_rt<R_OBJ>(P, DS, Xt, ld, row0 * T_SEP + threadIdx.x, T_SEP, ok, S);
+                nonmon_slow_rt<false>(P, Xt, ld, idx, acoef, S, nullptr, 0);
+            }
             for (int j = 0; j < P.m_mon; ++j) {
                 const double b = bcoef[j];
 #pragma unroll
@@ -166,7 +174,7 @@ cudaError_t ttm_launch_density_finish(const double* acc, const double* logt, dou
 
 cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* coeffs,
                                 double* S_out, const double* Xd, int64_t ldd, double* dS_out, int sm_count,
-                                cudaStream_t st) {
+                                cudaStream_t st, const double* base, double a0) {
     if (N == 0) return cudaSuccess;
     const int64_t rows = (N + T_SEP - 1) / T_SEP;
     int64_t grid = (rows + R_OBJ - 1) / R_OBJ;
@@ -176,7 +184,7 @@ cudaError_t ttm_launch_sep_eval(const PlanView& P, const double* Xt, int64_t ld,
         cudaError_t e = cudaFuncSetAttribute(sep_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    sep_eval_kernel<<<(unsigned)grid, T_SEP, smem, st>>>(P, Xt, ld, N, coeffs, S_out, Xd, ldd, dS_out);
+    sep_eval_kernel<<<(unsigned)grid, T_SEP, smem, st>>>(P, Xt, ld, N, coeffs, S_out, Xd, ldd, dS_out, base, a0);
     return cudaGetLastError();
 }
 

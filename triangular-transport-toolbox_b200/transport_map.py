@@ -643,10 +643,79 @@ class transport_map():
             # NB the reference ignores a user-supplied X when standardize_samples is False (tm.py:2419-2422)
             Xt, n = self._Xt, self._N
         Zt = self._empty(self.D, n)
+        gm = self._map_gemm_static() if n >= 4096 else None
+        if gm is not None:
+            # wide separable map: the nonmonotone sums of ALL components are one block-triangular FP64 GEMM (K-inv-rect
+            # on DMMA); per component only the monotone terms of its own column remain
+            cat = np.concatenate([np.asarray(self.coeffs_nonmon[k], dtype=np.float64) for k in range(self.D)])
+            R = np.zeros(gm['r_size'])
+            R[gm['rdst']] = cat[gm['src']] * gm['sc']
+            cp, cs = gm['const_ptr'], gm['const_src']
+            Rd = self._upload(R)
+            base = self._empty(self.D, (n + 1) // 2 * 2)
+            st = self._stream()
+            B.check(self._lib.ttm_map_rect(self._ctx, B.c_void_p(Xt.data_ptr()), Xt.shape[1], n, self.D, gm['rows'],
+                                           gm['ns'], self.skip_dimensions, B.c_void_p(Rd.data_ptr()),
+                                           B.c_void_p(base.data_ptr()), base.shape[1], st))
+            for k in range(self.D):
+                self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
+                a0 = float(sum(cat[q] for q in cs[cp[k]:cp[k + 1]]))
+                B.check(self._lib.ttm_sep_eval_base(self._plans[k], B.c_void_p(Xt.data_ptr()), Xt.shape[1], n,
+                                                    B.c_void_p(base[k].data_ptr()), a0, B.c_void_p(Zt[k].data_ptr()), st))
+            return self._to_rowmajor(Zt, n, self.D)
         for k in range(self.D):
             self._set_coeffs(k, self.coeffs_nonmon[k], self.coeffs_mon[k])
             self._s_device(k, Xt, n, Zt[k])
         return self._to_rowmajor(Zt, n, self.D)
+
+    def _map_gemm_static(self):
+        """Packing indices of the forward map's GEMM operand (ttm_map_rect), or None when the map is outside its class:
+        separable, Hermite functions, >= 32 components, nonmonotone terms = constants + per-variable groups of order
+        <= 3 on predecessor columns (the class of K-inv-fused).  Cached until the plans are recompiled.
+        TTM_MAP_GEMM=0 keeps the per-component kernels."""
+        if self.monotonicity != 'separable monotonicity' or self.D < 32 or os.environ.get('TTM_MAP_GEMM', '1') == '0':
+            return None
+        from .plan import FAM_HERMITE_E
+        cache = self.__dict__.setdefault('_inv_pack_cache', {})
+        if 'map_gemm' in cache:
+            return cache['map_gemm']
+        cache['map_gemm'] = None
+        plans, skip = self._host_plans, self.skip_dimensions
+        if self._family != FAM_HERMITE_E or any(p.c != skip + k for k, p in enumerate(plans)):
+            return None
+        if any(p.n_slow or p.n_multi or p.dense_maxord > 3 for p in plans):
+            return None
+        used = set()
+        for p in plans:
+            for _, idx_row, _ in p.dense_groups:
+                used.update(int(q) for q in np.nonzero(idx_row >= 0)[0])
+        if used - {2, 3, 4, 5, 6, 7}:
+            return None
+        slots = [2, 5, 7] if used <= {2, 5, 7} else [2, 3, 4, 5, 6, 7]
+        ns, rows = len(slots), self._Dtot - 1
+        if rows <= 0:
+            return None
+        size = B.c_int64()
+        B.check(self._lib.ttm_inverse_rect_rpack_size(self.D, rows, ns, B.ctypes.byref(size)))
+        rp = (rows + 7) // 8 * 8
+        src, sc, rdst, const_src, const_ptr, off = [], [], [], [], [0], 0
+        for k, p in enumerate(plans):
+            for v, idx_row, sc_row in p.dense_groups:
+                if v >= skip + k:
+                    return None                                            # not a triangular dependency
+                for q, sl in enumerate(slots):
+                    if sl < len(idx_row) and idx_row[sl] >= 0:
+                        src.append(off + int(idx_row[sl]))
+                        sc.append(float(sc_row[sl]))
+                        rdst.append((((k // 128) * rp + v) * ns + q) * 128 + k % 128)
+            const_src += [off + int(q) for q in p.const_idx]
+            const_ptr.append(len(const_src))
+            off += p.m_non
+        cache['map_gemm'] = {'ns': ns, 'rows': rows, 'r_size': size.value, 'src': np.asarray(src, dtype=np.int64),
+                             'sc': np.asarray(sc), 'rdst': np.asarray(rdst, dtype=np.int64),
+                             'const_src': np.asarray(const_src, dtype=np.int64),
+                             'const_ptr': np.asarray(const_ptr, dtype=np.int64)}
+        return cache['map_gemm']
 
     # ================================================================== objective + gradient (IR)
     def _objgrad(self, coeffs, k):
