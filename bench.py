@@ -273,6 +273,31 @@ def inverse_metric(rank, world, dist, torch, with_cpu=False):
                                    'features, table search and interpolation not counted)'}}
         del base
         del Xw, Zt
+    # ---- forward map of the same C5 map (all 256 components) through map() with host arrays: GEMM form of the
+    # nonmonotone sums (ttm_map_rect) against the per-component kernels
+    fwd = None
+    if rank == 0:
+        nm = 400_000
+        Xm = synthetic_samples(nm, Dm, seed=300)
+        fwd = {'points': nm}
+        keep = {}
+        for label, flag in (('gemm', '1'), ('per_component', '0')):
+            os.environ['TTM_MAP_GEMM'] = flag
+            tm._inv_pack_cache.pop('map_gemm', None)
+            ts = []
+            for rep in range(2):
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                keep[label] = tm.map(Xm)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t)
+            fwd[label + '_e2e_s'] = min(ts)
+        os.environ.pop('TTM_MAP_GEMM', None)
+        tm._inv_pack_cache.pop('map_gemm', None)
+        fwd['points_per_s_e2e'] = nm / fwd['gemm_e2e_s']
+        fwd['max_rel_diff_gemm_vs_per_component'] = float(np.max(np.abs(keep['gemm'] - keep['per_component'])) /
+                                                          np.max(np.abs(keep['per_component'])))
+        del keep, Xm
     cpu = None
     parity = None
     if with_cpu and rank == 0 and world == 1:
@@ -290,6 +315,8 @@ def inverse_metric(rank, world, dist, torch, with_cpu=False):
             'scaling': 'weak', 'e2e': True}
     if dev is not None:
         out['device'] = dev
+    if fwd is not None:
+        out['forward_map'] = fwd
     if cpu is not None:
         out['cpu_baseline'] = cpu
         out['parity_max_abs'] = parity

@@ -183,7 +183,8 @@ int ttm_sep_objgrad(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, con
  * per plan may be outstanding. */
 int ttm_sep_objgrad_launch(ttm_plan* plan, const double* Xt, int64_t ld, int64_t N, const double* host_b, void* stream);
 int ttm_sep_objgrad_wait(ttm_plan* plan, double* host_out, void* stream);
-/* fun_mon_objective (tm.py:2978-3006) whole, for n components in one call: every K-sepobj launch is queued, then each
+/* fun_mon_objective (tm.py:2978-3006) whole, for n components in one call: ONE batched K-sepobj launch per 64
+ * components (blockIdx.y = component; the plans' descriptors are registered in a device array on first use), then each
  * result is collected and the reduced objective assembled on the host,
  *   fg[i][0]   = b^T A b / 2 - (sum_s log dS_s) / n_total + b^T c,
  *   fg[i][1+j] = (A b)_j - (sum_s dPsi_sj / dS_s) / n_total + c_j,

@@ -50,9 +50,10 @@ struct ttm_ctx {
     FusedComp* h_fused = nullptr;
     int fused_cap = 0;
     cudaEvent_t ev_fused = nullptr;
-    static constexpr int NSIDE = 8;  // side streams of ttm_sep_reduced_batch (independent components overlap)
-    cudaStream_t side[NSIDE] = {};
-    cudaEvent_t ev_side = nullptr;
+    // descriptors of the plans that took part in a batched K-sepobj launch (device array + host registry)
+    SepBatchItem* d_items = nullptr;
+    int items_cap = 0;
+    std::vector<ttm_plan*> items;   // slot -> plan (nullptr: free)
 };
 
 struct ttm_plan {
@@ -66,6 +67,8 @@ struct ttm_plan {
     double* d_out = nullptr;       // [1+m]
     double* d_partials = nullptr;  // [MAX_GRID][1+m]
     unsigned int* d_counter = nullptr;
+    int batch_slot = -1;           // index in ctx->items / ctx->d_items, -1: not registered
+    bool batch_uploaded = false;   // descriptor in ctx->d_items is current
     double* h_pin = nullptr;       // pinned staging [2*(1+m)]
     cudaEvent_t ev_h2d = nullptr;  // recorded after every H2D copy out of h_pin: the buffer is not rewritten before it
     double* h_res = nullptr;       // pinned + mapped [1+m] result mirror written by the kernels' last block, then
@@ -122,8 +125,7 @@ int ttm_ctx_destroy(ttm_ctx* c) {
     cudaFree(c->d_fused);
     if (c->h_fused) cudaFreeHost(c->h_fused);
     if (c->ev_fused) cudaEventDestroy(c->ev_fused);
-    for (cudaStream_t q : c->side) if (q) cudaStreamDestroy(q);
-    if (c->ev_side) cudaEventDestroy(c->ev_side);
+    cudaFree(c->d_items);
     delete c;
     return TTM_OK;
 }
@@ -270,6 +272,7 @@ int ttm_plan_update_doubles(ttm_plan* p, const double* host_dblob, int64_t n_dou
 int ttm_plan_destroy(ttm_plan* p) {
     if (!p) return TTM_OK;
     cudaSetDevice(p->ctx->device);
+    if (p->batch_slot >= 0 && p->batch_slot < (int)p->ctx->items.size()) p->ctx->items[p->batch_slot] = nullptr;
     cudaFree(p->d_ib); cudaFree(p->d_db); cudaFree(p->d_coeffs); cudaFree(p->d_out);
     cudaFree(p->d_partials); cudaFree(p->d_counter);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -550,45 +553,77 @@ int ttm_sep_reduced_batch(int n, ttm_plan* const* plans, const double* Xt, int64
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < i; ++j)
             if (plans[i] == plans[j]) return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: a plan may appear once per call");
-    // all launches first.  The components are independent: with more than one they go to side streams ordered after
-    // the caller's stream, so that the (small, latency-bound) kernels overlap instead of queueing.  Completion is
-    // observed by the host through each plan's result mirror, so nothing has to be joined back.
+    // all launches first: ONE kernel for up to 64 components (blockIdx.y = component).  Descriptors of the plans are
+    // registered in a device array on first use; per launch only the sequence numbers and the active list travel.
     ttm_ctx* c = n > 0 ? plans[0]->ctx : nullptr;
-    const bool fan = n > 1;
-    if (fan) {
+    if (n > 0) {
         CK(cudaSetDevice(c->device));
-        if (!c->ev_side) CK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
-        CK(cudaEventRecord(c->ev_side, (cudaStream_t)stream));
-    }
-    auto lane = [&](int i) -> cudaStream_t {
-        if (!fan) return (cudaStream_t)stream;
-        return c->side[i % ttm_ctx::NSIDE];
-    };
-    for (int i = 0; i < n; ++i) {
-        if (plans[i]->ctx != c) return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: plans of different contexts");
-        if (fan) {
-            cudaStream_t& q = c->side[i % ttm_ctx::NSIDE];
-            if (!q) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
-            if (i < ttm_ctx::NSIDE) CK(cudaStreamWaitEvent(q, c->ev_side, 0));
+        bool grew = false;
+        for (int i = 0; i < n; ++i) {
+            ttm_plan* p = plans[i];
+            if (p->ctx != c) return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: plans of different contexts");
+            if (p->view.m_dmon > p->m) return fail(TTM_ERR_ARG, "ttm_sep_reduced_batch: inconsistent plan");
+            if (p->batch_slot < 0) {
+                int slot = -1;
+                for (size_t q = 0; q < c->items.size(); ++q) if (!c->items[q]) { slot = (int)q; break; }
+                if (slot < 0) { slot = (int)c->items.size(); c->items.push_back(nullptr); }
+                c->items[slot] = p;
+                p->batch_slot = slot;
+                if (slot >= c->items_cap) grew = true;
+            }
         }
-        int rc = ttm_sep_objgrad_launch(plans[i], Xt, ld, N, host_b[i], lane(i));
-        if (rc) return rc;
+        if (grew) {                                      // (re)allocate: every live descriptor is uploaded again
+            CK(cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(c->d_items);
+            c->d_items = nullptr;
+            c->items_cap = (int)c->items.size() * 2 + 16;
+            CK(cudaMalloc(&c->d_items, sizeof(SepBatchItem) * c->items_cap));
+            for (ttm_plan* q : c->items) if (q) q->batch_uploaded = false;
+        }
+        for (size_t q = 0; q < c->items.size(); ++q) {
+            ttm_plan* p = c->items[q];
+            if (!p || p->batch_uploaded) continue;
+            SepBatchItem it;
+            it.P = p->view; it.b = p->h_pin; it.d_b = p->d_coeffs + p->view.m_non; it.partials = p->d_partials;
+            it.counter = p->d_counter; it.out = p->d_out; it.out_host = p->h_res; it.flag_host = p->h_flag;
+            CK(cudaMemcpy(c->d_items + q, &it, sizeof(it), cudaMemcpyHostToDevice));
+            p->batch_uploaded = true;
+        }
+    }
+    for (int i0 = 0; i0 < n; i0 += TTM_SEP_BATCH_MAX) {
+        const int na = (n - i0 < TTM_SEP_BATCH_MAX) ? n - i0 : TTM_SEP_BATCH_MAX;
+        SepBatchLaunch L;
+        int max_mm = 1;
+        for (int a = 0; a < na; ++a) {
+            ttm_plan* p = plans[i0 + a];
+            const int mm = p->view.m_dmon;
+            CK(cudaEventSynchronize(p->ev_h2d));         // h_pin free (an earlier asynchronous coefficient upload)
+            std::memcpy(p->h_pin, host_b[i0 + a], mm * sizeof(double));
+            p->seq += 1;
+            L.seq[a] = p->seq;
+            L.item[a] = p->batch_slot;
+            if (mm > max_mm) max_mm = mm;
+        }
+        cudaError_t e = ttm_launch_sepobj_batch(c->d_items, L, na, max_mm, Xt, ld, N, c->delta, MAX_GRID, c->sm_count,
+                                                (cudaStream_t)stream);
+        if (e == cudaErrorInvalidValue) return fail(TTM_ERR_LIMIT, "ttm_sep_reduced_batch: too many monotone terms for shared memory");
+        CK(e);
     }
     for (int i = 0; i < n; ++i) {                       // then collect; the m x m algebra runs while the others finish
         ttm_plan* p = plans[i];
         const int m = p->view.m_dmon;
         double* fg = host_fg[i];
-        int rc = wait_result(p, fg, 1 + m, lane(i));
+        int rc = wait_result(p, fg, 1 + m, (cudaStream_t)stream);
         if (rc) return rc;
-        const double *b = host_b[i], *A = host_A[i], *c = host_c[i];
+        const double *b = host_b[i], *A = host_A[i], *cv = host_c[i];
         double quad = 0.0, lin = 0.0;
         const double sumlog = fg[0];
         for (int r = 0; r < m; ++r) {
             double ab = 0.0;
             for (int q = 0; q < m; ++q) ab += A[(size_t)r * m + q] * b[q];
             quad += b[r] * ab;
-            lin += b[r] * c[r];
-            fg[1 + r] = ab - fg[1 + r] / n_total + c[r];
+            lin += b[r] * cv[r];
+            fg[1 + r] = ab - fg[1 + r] / n_total + cv[r];
         }
         fg[0] = quad / 2 - sumlog / n_total + lin;
     }

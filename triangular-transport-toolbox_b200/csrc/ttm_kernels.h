@@ -95,6 +95,25 @@ cudaError_t ttm_launch_gram(const PlanView& P, const double* Xt, int64_t ld, int
                             double* scratch, int64_t scratch_doubles, int sm_count, cudaStream_t st);
 
 // reduced separable objective: sum log dS, colsum(dPsi/dS) (reference: fun_mon_objective :2978-3018)
+// K-sepobj for several components in one launch
+#define TTM_SEP_BATCH_MAX 64
+struct SepBatchItem {
+    PlanView P;
+    const double* b;               // coefficients (mapped host memory, written by the host before the launch)
+    double* d_b;
+    double* partials;
+    unsigned int* counter;
+    double* out;
+    double* out_host;
+    unsigned long long* flag_host;
+};
+struct SepBatchLaunch {
+    unsigned long long seq[TTM_SEP_BATCH_MAX];
+    int item[TTM_SEP_BATCH_MAX];
+};
+cudaError_t ttm_launch_sepobj_batch(const SepBatchItem* d_items, const SepBatchLaunch& L, int nact, int max_mm,
+                                    const double* Xt, int64_t ld, int64_t N, double delta, int max_grid, int sm_count,
+                                    cudaStream_t st);
 cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, int64_t N, const double* b,
                               double* d_b, double delta, double* partials, unsigned int* counter, double* out,
                               double* out_host, unsigned long long* flag_host, unsigned long long seq, int max_grid,

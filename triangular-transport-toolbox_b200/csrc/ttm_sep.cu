@@ -80,11 +80,12 @@ __global__ void __launch_bounds__(T_SEP) sep_eval_kernel(const PlanView P, const
 // -------------------------------------------------------------------------------------------------
 // b may live in mapped pinned host memory (read once per block); the last block mirrors the result to host memory
 // and publishes the launch's sequence number after a system fence (no D2H copy, no stream synchronisation)
-__global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
-                                                       int64_t N, const double* __restrict__ b, double* __restrict__ d_b,
-                                                       double delta, double* __restrict__ partials, unsigned int* counter,
-                                                       double* __restrict__ out, double* out_host,
-                                                       unsigned long long* flag_host, unsigned long long seq) {
+__device__ __forceinline__ void sepobj_body(const PlanView& P, const double* __restrict__ Xt, int64_t ld, int64_t N,
+                                            const double* __restrict__ b, double* __restrict__ d_b, double delta,
+                                            double* __restrict__ partials, unsigned int* counter,
+                                            double* __restrict__ out, double* out_host,
+                                            unsigned long long* flag_host, unsigned long long seq,
+                                            const unsigned int bx, const unsigned int gx) {
     extern __shared__ double sm[];
     const int mm = P.m_dmon;
     double* s_b = sm;                 // [mm]
@@ -94,12 +95,12 @@ __global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const d
     for (int j = tid; j < mm; j += T_SEP) {
         const double bj = b[j];
         s_b[j] = bj + delta;
-        if (blockIdx.x == 0 && d_b) d_b[j] = bj;       // device copy of the coefficients (map / inverse use it)
+        if (bx == 0 && d_b) d_b[j] = bj;       // device copy of the coefficients (map / inverse use it)
     }
     for (int j = 0; j < mm; ++j) s_acc[j * T_SEP + tid] = 0.0;
     __syncthreads();
     double lacc = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * T_SEP + tid; i < N; i += (int64_t)gridDim.x * T_SEP) {
+    for (int64_t i = (int64_t)bx * T_SEP + tid; i < N; i += (int64_t)gx * T_SEP) {
         double dS = 0.0;
         for (int j = 0; j < mm; ++j) dS = fma(s_b[j], plan_term(P, P.o_dmon_ptr, P.o_dmon_fac, j, Xt, ld, i), dS);
         lacc += log(dS);
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const d
         if (lane == 0) s_red[warp * (1 + mm) + 1 + j] = v;
     }
     __syncthreads();
-    double* part = partials + (int64_t)blockIdx.x * (1 + mm);
+    double* part = partials + (int64_t)bx * (1 + mm);
     for (int j = tid; j < 1 + mm; j += T_SEP) {
         double v = 0.0;
         for (int w = 0; w < T_SEP / 32; ++w) v += s_red[w * (1 + mm) + j];
@@ -123,13 +124,13 @@ __global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const d
     __threadfence();
     __shared__ unsigned int s_last;
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (tid == 0) s_last = (atomicAdd(counter, 1u) == gx - 1) ? 1u : 0u;
     __syncthreads();
     if (s_last) {
         __threadfence();
         for (int j = tid; j < 1 + mm; j += T_SEP) {
             double v = 0.0;
-            for (unsigned int bk = 0; bk < gridDim.x; ++bk) v += __ldcg(partials + (int64_t)bk * (1 + mm) + j);
+            for (unsigned int bk = 0; bk < gx; ++bk) v += __ldcg(partials + (int64_t)bk * (1 + mm) + j);
             out[j] = v;
             if (out_host) out_host[j] = v;
         }
@@ -140,6 +141,27 @@ __global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const d
         }
         if (tid == 0) *counter = 0u;
     }
+}
+
+
+__global__ void __launch_bounds__(T_SEP) sepobj_kernel(const PlanView P, const double* __restrict__ Xt, int64_t ld,
+                                                       int64_t N, const double* __restrict__ b, double* __restrict__ d_b,
+                                                       double delta, double* __restrict__ partials, unsigned int* counter,
+                                                       double* __restrict__ out, double* out_host,
+                                                       unsigned long long* flag_host, unsigned long long seq) {
+    sepobj_body(P, Xt, ld, N, b, d_b, delta, partials, counter, out, out_host, flag_host, seq, blockIdx.x, gridDim.x);
+}
+
+// the same for several components in ONE launch (blockIdx.y selects the component): the lockstep L-BFGS-B rounds of a
+// separable fit evaluate every component that asked for (f, g) together; descriptors live in device memory, only the
+// launch's sequence numbers and the list of active components travel as kernel parameters
+__global__ void __launch_bounds__(T_SEP) sepobj_batch_kernel(const SepBatchItem* __restrict__ items,
+                                                             const __grid_constant__ SepBatchLaunch L,
+                                                             const double* __restrict__ Xt, int64_t ld, int64_t N,
+                                                             double delta) {
+    const SepBatchItem& it = items[L.item[blockIdx.y]];
+    sepobj_body(it.P, Xt, ld, N, it.b, it.d_b, delta, it.partials, it.counter, it.out, it.out_host, it.flag_host,
+                L.seq[blockIdx.y], blockIdx.x, gridDim.x);
 }
 
 // change-of-variables bookkeeping of the density evaluators (transport_map.py:2618-2644, :2680-2712)
@@ -205,6 +227,25 @@ cudaError_t ttm_launch_sepobj(const PlanView& P, const double* Xt, int64_t ld, i
     }
     sepobj_kernel<<<(unsigned)grid, T_SEP, smem, st>>>(P, Xt, ld, N, b, d_b, delta, partials, counter, out, out_host,
                                                        flag_host, seq);
+    return cudaGetLastError();
+}
+
+cudaError_t ttm_launch_sepobj_batch(const SepBatchItem* d_items, const SepBatchLaunch& L, int nact, int max_mm,
+                                    const double* Xt, int64_t ld, int64_t N, double delta, int max_grid, int sm_count,
+                                    cudaStream_t st) {
+    if (nact <= 0) return cudaSuccess;
+    int64_t gx = (N + T_SEP - 1) / T_SEP;
+    const int64_t share = (int64_t)sm_count * 8 / nact;
+    if (gx > share) gx = share;
+    if (gx > max_grid) gx = max_grid;
+    if (gx < 1) gx = 1;
+    const size_t smem = sizeof(double) * (size_t)(max_mm + max_mm * T_SEP + (T_SEP / 32) * (1 + max_mm));
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sepobj_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    sepobj_batch_kernel<<<dim3((unsigned)gx, (unsigned)nact), T_SEP, smem, st>>>(d_items, L, Xt, ld, N, delta);
     return cudaGetLastError();
 }
 
