@@ -41,17 +41,17 @@ UNIT = 'evals/s'
 def flops_per_eval(k, n, q=Q, m_mon=4, c_exp=30):
     """Algorithmic FP64 work of one eval, SURVEY.md 8(d): node loop Q*(8 + c_exp + m_m + 2 m_m + c_exp + 2 + 1 + 2 m_m)
     + x_<c part (c_exp + 18) k + epilogue 75 (c_log = 47), per sample.  c_exp = 30 is the survey's frozen cost of the
-    CUDA library exp; c_exp = 18 re-freezes it for the exp the kernel ships (ttm_exp.cuh: 8 FMA + 1 ADD + 1 MUL)."""
+    CUDA library exp; c_exp = 14 re-freezes it for the exp the kernel ships (ttm_exp.cuh: 6 FMA + 1 ADD + 1 MUL)."""
     mm = 3 if k == 0 else m_mon
     node = q * (8 + c_exp + mm + 2 * mm + c_exp + 2 + 1 + 2 * mm)
     return n * (node + (c_exp + 18) * k + 75)
 
 
 def flops_executed(k, n, q=Q):
-    """FP64 flops the shipped tile kernel actually executes per eval (SASS instruction mix, FMA = 2): node loop 31
-    instructions = 24 FMA + 7 MUL/ADD = 55 flop per node; Gram-mode sweep 23 instructions = 14 FMA + 9 = 37 flop per
+    """FP64 flops the shipped tile kernel actually executes per eval (SASS instruction mix, FMA = 2): node loop 27
+    instructions = 20 FMA + 7 MUL/ADD = 47 flop per node; Gram-mode sweep 21 instructions = 12 FMA + 9 = 33 flop per
     (sample, column); prologue + epilogue (two exp, log, division, slot algebra) ~300 flop per sample."""
-    return n * (55 * q + 37 * k + 300)
+    return n * (47 * q + 33 * k + 300)
 
 
 def bytes_per_eval(k, n):
@@ -754,7 +754,7 @@ def run_gpu(args):
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic_r2.json')))
         except Exception:
             pass
-        fl18 = sum(flops_per_eval(k, n, c_exp=18) for k in mine)
+        fl18 = sum(flops_per_eval(k, n, c_exp=14) for k in mine)
         flx = sum(flops_executed(k, n) for k in mine)
         achieved = fl / t_kernels / 1e12
         per_launch_traffic = traffic.get('per_launch_avg_bytes') if (n == N_FULL and world == 1) else None
@@ -767,7 +767,7 @@ def run_gpu(args):
                                peaks_fp64.get('clock_rate_mhz'), peaks_fp64.get('dmma_m8n8k4_tflops')),
             'peak_live_probe': fp64_peak_tflops,
             # the same time against two other flop counts: the survey formula re-frozen for the
-            # shipped exp (c_exp = 18 instead of the library's 30), and the flops the shipped SASS executes
+            # shipped exp (c_exp = 14 instead of the library's 30), and the flops the shipped SASS executes
             'achieved_refrozen': fl18 / t_kernels / 1e12, 'frac_refrozen': fl18 / t_kernels / 1e12 / fp64_peak,
             'achieved_executed': flx / t_kernels / 1e12, 'frac_executed': flx / t_kernels / 1e12 / fp64_peak,
             'ncu_pipe_fp64_active_pct': traffic.get('pipe_fp64_active_pct'),
@@ -780,7 +780,7 @@ def run_gpu(args):
                     'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback'},
             'per_k': {str(k): {'ms': kt[k] * 1e3, 'tflops': flops_per_eval(k, n) / kt[k] / 1e12,
                                'frac': flops_per_eval(k, n) / kt[k] / 1e12 / fp64_peak,
-                               'tflops_refrozen': flops_per_eval(k, n, c_exp=18) / kt[k] / 1e12,
+                               'tflops_refrozen': flops_per_eval(k, n, c_exp=14) / kt[k] / 1e12,
                                'tflops_executed': flops_executed(k, n) / kt[k] / 1e12,
                                'evals_per_s': 1.0 / kt[k]} for k in (0, 31, 63) if k in kt},
         }

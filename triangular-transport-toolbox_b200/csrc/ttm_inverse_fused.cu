@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TB, 3) inverse_fused_kernel(const InvFusedArgs
     extern __shared__ double smem[];
     constexpr int ROW = CB * NS;                 // doubles per coefficient row
     unsigned int* s_tab = reinterpret_cast<unsigned int*>(smem);   // exp table (64 words)
-    double* s_coef = smem + 32;                  // [2][VC][ROW]
+    double* s_coef = smem + ttm_exp32::TAB_DOUBLES;   // [2][VC][ROW]
     double* s_diag = s_coef + 2 * VC * ROW;      // [CB][ROW]
     double* s_coarse = s_diag + CB * ROW;        // [CB][33]: every stride-th table value of the block's components | tmax
     double* s_table = s_coarse + CB * 33;        // STAGE: [2][2 ntab]
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(TB, 2) inverse_rect_kernel(const InvRectArgs a
     constexpr int PPT = TS * VC / TB;            // (sample, variable) pairs per thread in the feature step
     extern __shared__ double smem[];
     unsigned int* s_tab = reinterpret_cast<unsigned int*>(smem);
-    double* sA = smem + 32;                      // [2][KR][AS]
+    double* sA = smem + ttm_exp32::TAB_DOUBLES;  // [2][KR][AS]
     double* sF = sA + 2 * KR * AS;               // [2][KR][FS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ws = warp & 1, wc = warp >> 1;
@@ -484,7 +484,7 @@ cudaError_t ttm_launch_inverse_rect(const InvRectArgs& a, int sm_count, cudaStre
     if (a.ns != 3 && a.ns != 6) return cudaErrorInvalidValue;
     const int64_t work = (a.N + TS - 1) / TS * ((a.ncomp + TC - 1) / TC);
     const int kr = (a.ns == 3 ? 8 : 4) * a.ns;
-    const size_t smem = sizeof(double) * (size_t)(32 + 2 * kr * (AS + FS));
+    const size_t smem = sizeof(double) * (size_t)(ttm_exp32::TAB_DOUBLES + 2 * kr * (AS + FS));
     cudaError_t e;
     auto launch = [&](auto kernel) -> cudaError_t {
         if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -508,7 +508,7 @@ cudaError_t ttm_launch_inverse_fused(const InvFusedArgs& a, int sm_count, cudaSt
     if (a.N == 0 || a.ncomp == 0) return cudaSuccess;
     if (a.ns != 3 && a.ns != 6) return cudaErrorInvalidValue;
     const int64_t tiles = (a.N + TB * SPT - 1) / (TB * SPT);
-    const size_t smem0 = sizeof(double) * (size_t)(32 + (2 * VC + CB) * CB * a.ns + CB * 33);
+    const size_t smem0 = sizeof(double) * (size_t)(ttm_exp32::TAB_DOUBLES + (2 * VC + CB) * CB * a.ns + CB * 33);
     const int stage = a.ntab <= 2048 ? 1 : 0;            // 2 x [values | abscissae] <= 64 KB next to the operands
     const size_t smem = smem0 + sizeof(double) * (stage ? 4 * (size_t)a.ntab : 0);
     cudaError_t e;

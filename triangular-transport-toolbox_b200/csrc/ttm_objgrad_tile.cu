@@ -16,7 +16,7 @@
 //                                  with node-only weights w tau^i; the node constants are KERNEL PARAMETERS
 //                                  (constant-bank operands indexed by the uniform loop counter), the exp table is 256
 //                                  bytes of shared memory read without bank conflicts (ttm_exp.cuh): the loop touches
-//                                  shared memory with 4 wavefronts per node and warp.  31 FP64 instructions per node.
+//                                  shared memory with 4 wavefronts per node and warp.  27 FP64 instructions per node.
 //   phase 2  (warp <-> columns)    ONE sweep over the columns x_<c: every warp owns the dense groups g = warp (mod 8)
 //                                  and walks the tile's 8 rows of 32 samples for them: S_non partial sums per sample
 //                                  (value) and, in the same pass, h_j = sum_i w_i psi_ij (gradient) accumulated
@@ -71,7 +71,7 @@ static_assert(sizeof(Layout) <= sizeof(((ObjArgs*)nullptr)->tile_lay), "ObjArgs:
 inline Layout make_layout(int m, int ndense, int ns, int nout, bool grad) {
     Layout L;
     int o = 0;
-    L.o_tab = o;   o += 32;                           // 64 words: exp table, low | high
+    L.o_tab = o;   o += ttm_exp32::TAB_DOUBLES;       // exp table: low words | high words
     L.o_coef = o;  o += (m + 2) & ~1;
     L.o_prod = o;  o += 8 * ndense;                   // coefficient * scale, slot 2*order+hf
     L.o_col = o;   o += (ndense + 2) / 2;             // ints
