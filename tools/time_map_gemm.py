@@ -38,6 +38,7 @@ for mode in ('1', '0'):
         ts.append(time.perf_counter() - t)
     res[mode] = Z
     out['e2e_s_gemm' if mode == '1' else 'e2e_s_per_component'] = min(ts)
+    out['e2e_all_' + mode] = [round(t, 4) for t in ts]
 out['max_rel_diff'] = float(np.max(np.abs(res['1'] - res['0'])) / np.max(np.abs(res['0'])))
 # device-resident: kernels only
 Xt = tm._to_colmajor(X, tm._mean_d, tm._std_d)
