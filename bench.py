@@ -72,6 +72,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu_index, self.samples, self.active = gpu_index, [], False
+        self.nearby = []            # samples outside the timed window (the GPU is busy before and after it as well)
+        self.t_on = self.t_off = None
         self.proc = None
 
     def run(self):
@@ -82,8 +84,8 @@ class ClockSampler(threading.Thread):
                                          stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 p = [t.strip() for t in line.split(',')]
-                if len(p) >= 8 and p[0] == str(self.gpu_index) and self.active:
-                    self.samples.append(p)
+                if len(p) >= 8 and p[0] == str(self.gpu_index):
+                    (self.samples if self.active else self.nearby).append((time.perf_counter(), p))
         except Exception:
             pass
 
@@ -92,15 +94,22 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
 
     def summary(self):
-        if not self.samples:
+        use, pad = [p for _, p in self.samples], 0.0
+        if len(use) < 2 and self.t_on is not None:
+            # the timed window is shorter than the sampling period (multi-GPU runs: ~50 ms): take the samples within
+            # 0.3 s around it -- the per-launch pass before and the fit after keep the GPU under the same load
+            pad = 0.3
+            use += [p for t, p in self.nearby if self.t_on - pad <= t <= (self.t_off or t) + pad]
+        if not use:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        sm = sorted(float(s[1]) for s in self.samples)
+        sm = sorted(float(s[1]) for s in use)
         reasons = []
         for idx, name in ((4, 'hw_slowdown'), (5, 'hw_thermal_slowdown'), (6, 'sw_thermal_slowdown'), (7, 'sw_power_cap')):
-            if any(s[idx].lower().startswith('active') for s in self.samples):
+            if any(s[idx].lower().startswith('active') for s in use):
                 reasons.append(name)
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][2]),
-                'power_w_max': max(float(s[3]) for s in self.samples), 'reasons': reasons, 'samples': len(sm)}
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(use[0][2]),
+                'power_w_max': max(float(s[3]) for s in use), 'reasons': reasons, 'samples': len(sm),
+                'samples_in_window': len(self.samples), 'window_padding_s': pad}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -624,6 +633,7 @@ def run_gpu(args):
         join()
     barrier()
     sampler.active = True
+    sampler.t_on = time.perf_counter()
     t_steps = []
     wall0 = time.perf_counter()
     for s in range(args.steps):
@@ -679,7 +689,7 @@ def run_gpu(args):
     B.check(lib.ttm_ctx_set_blocks_per_sm(tm._ctx, 0))
     barrier()
     sampler.active = False
-    sampler.stop()
+    sampler.t_off = time.perf_counter()
 
     fp64_peak_tflops = tm.fp64_peak_tflops() if rank == 0 else 0.0
 
@@ -707,6 +717,8 @@ def run_gpu(args):
                'slowest_component_rank0': max(({'k': k, **tm._fit_info[k]} for k in mine), key=lambda r: r['seconds'])}
         if world > 1:
             fit['coefficients_identical_across_ranks'] = coefficients_identical_across_ranks(tm, dist, torch)
+    time.sleep(0.12)                                   # one more sampling period under the fit's tail
+    sampler.stop()
     multi = multi_gpu_check(rank, world, dist, torch) if world > 1 else None
 
     tt = torch.tensor([t_local, t_e2e_local], dtype=torch.float64, device='cuda')
