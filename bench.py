@@ -717,7 +717,6 @@ def run_gpu(args):
                'slowest_component_rank0': max(({'k': k, **tm._fit_info[k]} for k in mine), key=lambda r: r['seconds'])}
         if world > 1:
             fit['coefficients_identical_across_ranks'] = coefficients_identical_across_ranks(tm, dist, torch)
-    time.sleep(0.12)                                   # one more sampling period under the fit's tail
     sampler.stop()
     multi = multi_gpu_check(rank, world, dist, torch) if world > 1 else None
 
