@@ -122,3 +122,81 @@ def test_donor_map_equals_the_all_pairs_definition():
             # identical lists at different positions may share a donor where the all-pairs search kept k itself
             assert got[k] == want[k] or (non[got[k]][:len(non[k])] == non[k] and len(non[got[k]]) >= len(non[want[k]])), k
             assert non[got[k]][:len(non[k])] == non[k]
+
+
+@pytest.mark.parametrize('D,E,mixed', [(20, 3, False), (21, 9, True), (150, 5, False)])
+def test_packed_operands_of_the_fused_kernels_reproduce_the_nonmonotone_sums(D, E, mixed):
+    """plan.pack_fused_operands (Apack of K-inv-fused, Rpack of K-inv-rect / K-map-rect): contracting the packed
+    coefficient*scale with the features the kernels form ({He1, He2 e, He3 e} or the 6-slot set) must reproduce the
+    oracle's nonmonotone part  Psi_non a  of every component -- block layout, triangular zero padding, slot order,
+    Hermite-function scales and the split between the conditioning block (Rpack) and the solved columns."""
+    from cases import c5_terms, synthetic_samples, headline_sep_coeffs
+    from ttt_b200 import plan as PL
+    mon, non = c5_terms(D)
+    if mixed:
+        non = [[[]] + [t for j in range(k) for t in ([j], [j, 'HF'], [j, j], [j, j, 'HF'], [j, j, j], [j, j, j, 'HF'])]
+               for k in range(D)]
+    X = synthetic_samples(300, D, seed=31)
+    kw = dict(monotone=mon, nonmonotone=non, monotonicity='separable monotonicity')
+    om = OracleMap(X=X.copy(), **kw)
+    fam, polyfunc, polyder, _ = resolve_family('hermite function')
+    plans = [ComponentPlan(k, k, D, fam, polyfunc, polyder, mon[k], non[k], om.special_terms, None) for k in range(D)]
+    cm, cn = headline_sep_coeffs(mon, non)
+    Xs = om.X                                                   # standardised samples, as the kernels see them
+    n = Xs.shape[0]
+
+    def feats(x, ns):
+        ga = np.exp(-0.25 * x * x)
+        P2, P3 = x * x - 1.0, x * (x * x - 3.0)
+        return [x, P2 * ga, P3 * ga] if ns == 3 else [x, x * ga, P2, P2 * ga, P3, P3 * ga]
+
+    # --- conditional inverse: components E .. D-1, split at E
+    sub = plans[E:]
+    st = PL.pack_fused_operands(sub, E, E)
+    assert st is not None and st['ns'] == (6 if mixed else 3)
+    ns, CB, ncomp = st['ns'], PL.FUSED_CB, D - E
+    cat = np.concatenate([cn[k] for k in range(E, D)])
+    val = cat[st['src']] * st['sc']
+    A = np.zeros(PL.fused_apack_doubles(ncomp, E, ns))
+    A[st['dst']] = val
+    R = np.zeros(PL.rect_rpack_doubles(ncomp, E, ns))
+    R[st['rdst']] = val[st['rkeep']]
+    rp = (E + 7) // 8 * 8
+    for j in (0, 1, ncomp // 2, ncomp - 1):
+        k = E + j
+        want = om.Psi_nonmon[k] @ cn[k]
+        a0 = sum(cat[q] for q in st['const_src'][st['const_ptr'][j]:st['const_ptr'][j + 1]])
+        b, jj = divmod(j, CB)
+        row0 = b * (E + CB) + CB * b * (b - 1) // 2
+        walk_all = np.full(n, a0)
+        for v in range(min(D, E + CB * b + CB)):               # the rows block b holds (zero beyond the predecessors)
+            f = feats(Xs[:, v], ns)
+            for q in range(ns):
+                walk_all += f[q] * A[((row0 + v) * CB + jj) * ns + q]
+        assert rel_err(walk_all, want) <= 1e-12, (j, 'Apack')
+        # split: Rpack carries the columns < E, the walk (same Apack rows) the columns >= E
+        base = np.zeros(n)
+        for v in range(E):
+            f = feats(Xs[:, v], ns)
+            for q in range(ns):
+                base += f[q] * R[(((j // 128) * rp + v) * ns + q) * 128 + j % 128]
+        walk = np.full(n, a0)
+        for v in range(E, min(D, E + CB * b + CB)):
+            f = feats(Xs[:, v], ns)
+            for q in range(ns):
+                walk += f[q] * A[((row0 + v) * CB + jj) * ns + q]
+        assert rel_err(base + walk, want) <= 1e-12, (j, 'Rpack + Apack')
+    # --- forward map: all components, every predecessor column in Rpack
+    gm = PL.pack_fused_operands(plans, 0, D - 1, want_apack=False)
+    cat = np.concatenate(cn)
+    Rm = np.zeros(PL.rect_rpack_doubles(D, D - 1, gm['ns']))
+    Rm[gm['rdst']] = (cat[gm['src']] * gm['sc'])[gm['rkeep']]
+    rp = (D - 1 + 7) // 8 * 8
+    for k in (0, 1, D // 2, D - 1):
+        a0 = sum(cat[q] for q in gm['const_src'][gm['const_ptr'][k]:gm['const_ptr'][k + 1]])
+        got = np.full(n, a0)
+        for v in range(D - 1):
+            f = feats(Xs[:, v], gm['ns'])
+            for q in range(gm['ns']):
+                got += f[q] * Rm[(((k // 128) * rp + v) * gm['ns'] + q) * 128 + k % 128]
+        assert rel_err(got, om.Psi_nonmon[k] @ cn[k]) <= 1e-12, (k, 'map Rpack')

@@ -49,7 +49,7 @@ tm._inv_pack_cache.pop('map_gemm', None)
 gm = tm._map_gemm_static()
 cat = np.concatenate([np.asarray(tm.coeffs_nonmon[k], dtype=np.float64) for k in range(D)])
 R = np.zeros(gm['r_size'])
-R[gm['rdst']] = cat[gm['src']] * gm['sc']
+R[gm['rdst']] = (cat[gm['src']] * gm['sc'])[gm['rkeep']]
 Rd = tm._upload(R)
 base = tm._empty(D, (n + 1) // 2 * 2)
 st = tm._stream()

@@ -417,3 +417,75 @@ def donor_map(nonmonotone):
         else:
             roots.append(k)
     return dm
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Packed operands of the fused kernels (host side, pure numpy: tested on the CPU against the oracle's basis)
+# ---------------------------------------------------------------------------------------------------------------------
+FUSED_CB = 16            # components per block of K-inv-fused (ttm_inverse_fused.cu: CB)
+RECT_TC = 128            # components per tile of K-inv-rect (ttm_inverse_fused.cu: TC)
+
+
+def fused_slots(plans):
+    """Slot list (bit 2*order + hf of a dense group) shared by the components, or None when a component is outside the
+    class of the fused kernels: nonmonotone terms = constants + per-variable groups of order <= 3."""
+    if any(p.n_slow or p.n_multi or p.dense_maxord > 3 for p in plans):
+        return None
+    used = set()
+    for p in plans:
+        for _, idx_row, _ in p.dense_groups:
+            used.update(int(q) for q in np.nonzero(idx_row >= 0)[0])
+    if used - {2, 3, 4, 5, 6, 7}:
+        return None
+    return [2, 5, 7] if used <= {2, 5, 7} else [2, 3, 4, 5, 6, 7]
+
+
+def fused_apack_doubles(ncomp, c0, ns):
+    """Size of Apack (ttm_inverse_fused_apack_size): block b holds the rows v = 0 .. c0 + 16 b + 15."""
+    nblk = (ncomp + FUSED_CB - 1) // FUSED_CB
+    return (nblk * (c0 + FUSED_CB) + FUSED_CB * nblk * (nblk - 1) // 2) * FUSED_CB * ns
+
+
+def rect_rpack_doubles(ncomp, rows, ns):
+    """Size of Rpack (ttm_inverse_rect_rpack_size): [ceil(ncomp/128)][rows rounded up to 8][ns][128]."""
+    return ((ncomp + RECT_TC - 1) // RECT_TC) * ((rows + 7) // 8 * 8) * ns * RECT_TC
+
+
+def pack_fused_operands(plans, first_col, rect_rows, want_apack=True):
+    """Scatter indices of coefficient*scale into the packed operands of K-inv-fused (Apack) and K-inv-rect / K-map-rect
+    (Rpack) for the components `plans` (component j solves / evaluates column first_col + j).
+
+    rect_rows: number of leading variables whose contribution goes into Rpack (0: none; the conditioning width E for
+    the split inverse; Dtot - 1 for the forward map).  Returns None when the class does not fit, else a dict with
+      ns, slots, src (index into the concatenated coefficients_nonmon of the components), sc (scale),
+      dst (index into Apack, if want_apack), rdst / rkeep (index into Rpack for the entries with v < rect_rows),
+      const_src / const_ptr (CSR of the constant terms of each component: a0_j = sum of those coefficients)."""
+    slots = fused_slots(plans)
+    if slots is None or any(p.c != first_col + j for j, p in enumerate(plans)):
+        return None
+    ns, CB = len(slots), FUSED_CB
+    rp = (rect_rows + 7) // 8 * 8
+    dst, src, sc, rdst, const_src, const_ptr, off = [], [], [], [], [], [0], 0
+    for j, p in enumerate(plans):
+        b, jj = divmod(j, CB)
+        row0 = b * (first_col + CB) + CB * b * (b - 1) // 2
+        for v, idx_row, sc_row in p.dense_groups:
+            if v >= first_col + j:
+                return None                                                # not a triangular dependency
+            for q, sl in enumerate(slots):
+                if sl < len(idx_row) and idx_row[sl] >= 0:
+                    dst.append(((row0 + v) * CB + jj) * ns + q)
+                    src.append(off + int(idx_row[sl]))
+                    sc.append(float(sc_row[sl]))
+                    rdst.append((((j // RECT_TC) * rp + v) * ns + q) * RECT_TC + j % RECT_TC if v < rect_rows else -1)
+        const_src += [off + int(q) for q in p.const_idx]
+        const_ptr.append(len(const_src))
+        off += p.m_non
+    rdst = np.asarray(rdst, dtype=np.int64)
+    rkeep = rdst >= 0
+    out = {'ns': ns, 'slots': slots, 'src': np.asarray(src, dtype=np.int64), 'sc': np.asarray(sc, dtype=np.float64),
+           'rdst': rdst[rkeep], 'rkeep': rkeep, 'const_src': np.asarray(const_src, dtype=np.int64),
+           'const_ptr': np.asarray(const_ptr, dtype=np.int64)}
+    if want_apack:
+        out['dst'] = np.asarray(dst, dtype=np.int64)
+    return out

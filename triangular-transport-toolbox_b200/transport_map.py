@@ -649,7 +649,7 @@ class transport_map():
             # on DMMA); per component only the monotone terms of its own column remain
             cat = np.concatenate([np.asarray(self.coeffs_nonmon[k], dtype=np.float64) for k in range(self.D)])
             R = np.zeros(gm['r_size'])
-            R[gm['rdst']] = cat[gm['src']] * gm['sc']
+            R[gm['rdst']] = (cat[gm['src']] * gm['sc'])[gm['rkeep']]
             cp, cs = gm['const_ptr'], gm['const_src']
             Rd = self._upload(R)
             base = self._empty(self.D, (n + 1) // 2 * 2)
@@ -675,47 +675,23 @@ class transport_map():
         TTM_MAP_GEMM=0 keeps the per-component kernels."""
         if self.monotonicity != 'separable monotonicity' or self.D < 32 or os.environ.get('TTM_MAP_GEMM', '1') == '0':
             return None
-        from .plan import FAM_HERMITE_E
+        from .plan import FAM_HERMITE_E, pack_fused_operands, rect_rpack_doubles
         cache = self.__dict__.setdefault('_inv_pack_cache', {})
         if 'map_gemm' in cache:
             return cache['map_gemm']
         cache['map_gemm'] = None
-        plans, skip = self._host_plans, self.skip_dimensions
-        if self._family != FAM_HERMITE_E or any(p.c != skip + k for k, p in enumerate(plans)):
+        rows = self._Dtot - 1
+        if self._family != FAM_HERMITE_E or rows <= 0:
             return None
-        if any(p.n_slow or p.n_multi or p.dense_maxord > 3 for p in plans):
-            return None
-        used = set()
-        for p in plans:
-            for _, idx_row, _ in p.dense_groups:
-                used.update(int(q) for q in np.nonzero(idx_row >= 0)[0])
-        if used - {2, 3, 4, 5, 6, 7}:
-            return None
-        slots = [2, 5, 7] if used <= {2, 5, 7} else [2, 3, 4, 5, 6, 7]
-        ns, rows = len(slots), self._Dtot - 1
-        if rows <= 0:
+        gm = pack_fused_operands(self._host_plans, self.skip_dimensions, rows, want_apack=False)
+        if gm is None:
             return None
         size = B.c_int64()
-        B.check(self._lib.ttm_inverse_rect_rpack_size(self.D, rows, ns, B.ctypes.byref(size)))
-        rp = (rows + 7) // 8 * 8
-        src, sc, rdst, const_src, const_ptr, off = [], [], [], [], [0], 0
-        for k, p in enumerate(plans):
-            for v, idx_row, sc_row in p.dense_groups:
-                if v >= skip + k:
-                    return None                                            # not a triangular dependency
-                for q, sl in enumerate(slots):
-                    if sl < len(idx_row) and idx_row[sl] >= 0:
-                        src.append(off + int(idx_row[sl]))
-                        sc.append(float(sc_row[sl]))
-                        rdst.append((((k // 128) * rp + v) * ns + q) * 128 + k % 128)
-            const_src += [off + int(q) for q in p.const_idx]
-            const_ptr.append(len(const_src))
-            off += p.m_non
-        cache['map_gemm'] = {'ns': ns, 'rows': rows, 'r_size': size.value, 'src': np.asarray(src, dtype=np.int64),
-                             'sc': np.asarray(sc), 'rdst': np.asarray(rdst, dtype=np.int64),
-                             'const_src': np.asarray(const_src, dtype=np.int64),
-                             'const_ptr': np.asarray(const_ptr, dtype=np.int64)}
-        return cache['map_gemm']
+        B.check(self._lib.ttm_inverse_rect_rpack_size(self.D, rows, gm['ns'], B.ctypes.byref(size)))
+        assert size.value == rect_rpack_doubles(self.D, rows, gm['ns'])
+        gm.update(rows=rows, r_size=size.value)
+        cache['map_gemm'] = gm
+        return gm
 
     # ================================================================== objective + gradient (IR)
     def _objgrad(self, coeffs, k):
@@ -1165,65 +1141,34 @@ class transport_map():
 
     def _inverse_fused_static(self, ks, mode):
         """The part of the K-inv-fused / K-inv-rect operands that depends on the term lists only (class check, slot set,
-        packed destination of every coefficient), cached until the plans are recompiled: a conditional-sampling loop
-        with changing coefficients (EnTF cycles, adaptation) pays one gather/scatter per call instead of a walk over
-        every dense group of every component."""
-        from .plan import FAM_HERMITE_E
+        packed destination of every coefficient: plan.pack_fused_operands), cached until the plans are recompiled: a
+        conditional-sampling loop with changing coefficients (EnTF cycles, adaptation) pays one gather/scatter per call
+        instead of a walk over every dense group of every component."""
+        from .plan import FAM_HERMITE_E, pack_fused_operands, fused_apack_doubles, rect_rpack_doubles
         cache = self.__dict__.setdefault('_inv_pack_cache', {})
         skey = (tuple(ks), mode)
         if skey in cache:
             return cache[skey]
         cache[skey] = None
         plans = [self._host_plans[k] for k in ks]
-        c0 = plans[0].c
-        if self._family != FAM_HERMITE_E or any(p.c != c0 + j for j, p in enumerate(plans)):
+        c0, ncomp = plans[0].c, len(ks)
+        if self._family != FAM_HERMITE_E:
             return None
-        if any(p.n_slow or p.n_multi or p.dense_maxord > 3 for p in plans):
-            return None
-        used = set()
-        for p in plans:
-            for _, idx_row, _ in p.dense_groups:
-                used.update(int(s) for s in np.nonzero(idx_row >= 0)[0])
-        if used - {2, 3, 4, 5, 6, 7}:
-            return None
-        slots = [2, 5, 7] if used <= {2, 5, 7} else [2, 3, 4, 5, 6, 7]     # bit 2*order+hf, as in the tile kernel
-        ns, CB, ncomp = len(slots), 16, len(ks)
-        size = B.c_int64()
-        B.check(self._lib.ttm_inverse_fused_apack_size(ncomp, c0, ns, B.ctypes.byref(size)))
-        a_size = size.value
         # wide conditioning block: its share of the offsets is one GEMM (K-inv-rect) ahead of the sequential walk
         split = c0 > 0 and mode != '0' and (mode == '1' or (c0 >= 32 and ncomp >= 32))
-        c0p = (c0 + 7) // 8 * 8
-        r_size = 0
+        st = pack_fused_operands(plans, c0, c0 if split else 0)
+        if st is None:
+            return None
+        size = B.c_int64()
+        B.check(self._lib.ttm_inverse_fused_apack_size(ncomp, c0, st['ns'], B.ctypes.byref(size)))
+        assert size.value == fused_apack_doubles(ncomp, c0, st['ns'])
+        st.update(ncomp=ncomp, c0=c0, split=split, a_size=size.value, r_size=0)
         if split:
-            B.check(self._lib.ttm_inverse_rect_rpack_size(ncomp, c0, ns, B.ctypes.byref(size)))
-            r_size = size.value
-        dst, src, sc, rdst, const_src, const_ptr = [], [], [], [], [], [0]
-        off = 0                                                            # offset of component j in the concatenated coefficients
-        for j, (k, p) in enumerate(zip(ks, plans)):
-            b, jj = divmod(j, CB)
-            row0 = b * (c0 + CB) + CB * b * (b - 1) // 2
-            for v, idx_row, sc_row in p.dense_groups:
-                if v >= c0 + j:
-                    return None                                            # not a triangular dependency
-                for q, sl in enumerate(slots):
-                    if sl < len(idx_row) and idx_row[sl] >= 0:
-                        dst.append(((row0 + v) * CB + jj) * ns + q)
-                        src.append(off + int(idx_row[sl]))
-                        sc.append(float(sc_row[sl]))
-                        # K-inv-rect operand [j // 128][v][slot][j % 128]; -1: a column the walk itself solves
-                        rdst.append((((j // 128) * c0p + v) * ns + q) * 128 + j % 128 if v < c0 else -1)
-            const_src += [off + int(q) for q in p.const_idx]
-            const_ptr.append(len(const_src))
-            off += p.m_non
-        rdst = np.asarray(rdst, dtype=np.int64)
-        rkeep = rdst >= 0
-        cache[skey] = {'ncomp': ncomp, 'c0': c0, 'ns': ns, 'split': split, 'a_size': a_size, 'r_size': r_size,
-                       'dst': np.asarray(dst, dtype=np.int64), 'src': np.asarray(src, dtype=np.int64),
-                       'sc': np.asarray(sc), 'rdst': rdst[rkeep], 'rkeep': rkeep,
-                       'const_src': np.asarray(const_src, dtype=np.int64),
-                       'const_ptr': np.asarray(const_ptr, dtype=np.int64)}
-        return cache[skey]
+            B.check(self._lib.ttm_inverse_rect_rpack_size(ncomp, c0, st['ns'], B.ctypes.byref(size)))
+            assert size.value == rect_rpack_doubles(ncomp, c0, st['ns'])
+            st['r_size'] = size.value
+        cache[skey] = st
+        return st
 
     def _inverse_fused_setup(self, comps, resolution=1001):
         """Operands of K-inv-fused (ttm_inverse_fused: the component loop of tm.py:3684-3698 in one launch), or None if
