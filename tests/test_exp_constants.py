@@ -40,7 +40,7 @@ def test_table_holds_correctly_rounded_powers(entries):
         assert abs(got - exact) <= abs(exact) * mp.mpf(2) ** -53, j     # half an ulp
 
 
-@pytest.mark.parametrize('variant,bound', [(64, 7e-15), (32, 5e-16)])
+@pytest.mark.parametrize('variant,bound', [(64, 7e-15), (32, 1e-15)])
 def test_reduction_and_polynomial_stay_within_the_stated_error(variant, bound):
     m = macros(variant)
     E = variant
