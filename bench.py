@@ -229,7 +229,9 @@ def inverse_metric(rank, world, dist, torch, with_cpu=False):
         dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        res[mode] = {'samples_per_s': n_use * world / float(dt[0]), 'samples': n_use * world, 'seconds': float(dt[0])}
+        res[mode] = {'samples_per_s': n_use * world / float(dt[0]), 'samples': n_use * world, 'seconds': float(dt[0]),
+                     # bytes that cross PCIe per call (Z and X* in, the solved columns out), all ranks together
+                     'host_device_gbs': 8.0 * n_use * world * (E + 2 * (Dm - E)) / float(dt[0]) / 1e9}
         if not alt:
             resid = float(np.max(np.abs(tm.map(Xs[:20000])[:, E:] - Z[:20000])))
             res[mode]['max_residual'] = resid
