@@ -179,10 +179,19 @@ __global__ void __launch_bounds__(T_BAS) basis_dense_kernel(const PlanView P, co
                     last_col = col; cur = 0; pc = 1.0; pm = 0.0; have_ga = false;
                 }
                 if (o < cur) { cur = 0; pc = 1.0; pm = 0.0; }   // orders usually ascend within a variable
-                for (; cur < o; ++cur) {         // three-term recurrence of the family up to order o
-                    double A, B, C;
-                    rec_coef(family, cur, A, B, C);
-                    const double pn = fma(fma(A, x, B), pc, -C * pm);
+                // three-term recurrence of the family up to order o: one step per term in the usual term order, so the
+                // loop is NOT unrolled (ptxas' 16-way unrolling with its trip-count prologue tripled the instructions
+                // executed per term; the kernel is issue-bound)
+#pragma unroll 1
+                for (; cur < o; ++cur) {
+                    double pn;
+                    if (FAM == FAM_HERMITE_E) {  // A = 1, B = 0, C = cur
+                        pn = fma(x, pc, -(double)cur * pm);
+                    } else {
+                        double A, B, C;
+                        rec_coef(family, cur, A, B, C);
+                        pn = fma(fma(A, x, B), pc, -C * pm);
+                    }
                     pm = pc; pc = pn;
                 }
                 v = s_scale[j0 + t] * pc;
