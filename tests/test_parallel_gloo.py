@@ -55,3 +55,62 @@ def test_allgather_of_coefficients_world_size_2():
         ret = mgr.dict()
         mp.spawn(_worker, args=(size, port, ret), nprocs=size, join=True)
         assert all(ret.get(r) for r in range(size))
+
+
+def _lockstep_worker(rank, size, port, ret):
+    """Sample-sharded separable fit, host side: every rank holds a shard of the samples, each evaluation all-reduces
+    the partial sums (sum log dS, sum dPsi / dS) and the ranks advance the SAME L-BFGS-B iteration in lockstep
+    (transport_map._fit_separable_lockstep with sample_sharded=True; the sums come from K-sepobj there, from numpy
+    here).  Every rank must end on the single-process fit."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    from ttt_b200 import hostopt
+    rng = np.random.default_rng(11)
+    n, comps = 600, 3
+    probs = []
+    for c in range(comps):
+        m = 2 + c
+        dPsi = np.abs(rng.standard_normal((n, m))) + 0.1            # derivative basis (positive)
+        A = rng.standard_normal((m, m))
+        A = A @ A.T / m + 0.2 * np.eye(m)
+        probs.append((dPsi, A, 1e-8 * A.sum(axis=1), rng.uniform(0.2, 1.0, m)))
+    lo, hi = rank * n // size, (rank + 1) * n // size
+
+    def sums(c, b, rows):
+        dPsi = probs[c][0][rows]
+        dS = dPsi @ (b + 1e-8)
+        return np.concatenate(([np.sum(np.log(dS))], (dPsi / dS[:, None]).sum(axis=0)))
+
+    def assemble(c, b, out):
+        _, A, bvec, _ = probs[c]
+        Ax = A @ b
+        return b @ Ax / 2 - out[0] / n + b @ bvec, Ax - out[1:] / n + bvec
+
+    held = {}
+
+    def launch(i, b):
+        held[i] = np.array(b)
+
+    def collect(i):
+        return assemble(i, held[i], allreduce_sum(sums(i, held[i], slice(lo, hi))))
+
+    bounds = [(np.zeros(len(p[3])), np.full(len(p[3]), np.inf)) for p in probs]
+    got = hostopt.lbfgsb_lockstep([p[3] for p in probs], bounds, launch, collect)
+    whole = hostopt.lbfgsb_lockstep([p[3] for p in probs], bounds, lambda i, b: held.__setitem__(i, np.array(b)),
+                                    lambda i: assemble(i, held[i], sums(i, held[i], slice(0, n))))
+    ok = all(np.allclose(g.x, w.x, rtol=1e-9, atol=1e-12) and g.status == 0 for g, w in zip(got, whole))
+    # identical iterates on every rank (the all-reduced sums are the same numbers everywhere)
+    flat = np.concatenate([g.x for g in got])
+    both = [torch.zeros(flat.size, dtype=torch.float64) for _ in range(size)]
+    dist.all_gather(both, torch.from_numpy(flat))
+    ok = ok and all(torch.equal(both[0], t) for t in both)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sample_sharded_lockstep_fit_world_size_2():
+    size, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_lockstep_worker, args=(size, port, ret), nprocs=size, join=True)
+        assert all(ret.get(r) for r in range(size))
